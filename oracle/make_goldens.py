@@ -1,0 +1,275 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (TEST INFRASTRUCTURE).
+
+Run in the build container only (needs /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_goldens.py
+
+Shims, all applied from outside the reference sources:
+  * neural_nets.models.vgg19 -> seeded weights=None torchvision VGG19 (the hard-coded
+    pretrained download at neural_nets.py:19 cannot run offline);
+  * NeuralStyleTransfer replaced by a capturing stub when only the init image is wanted.
+The GPU box has no /root/reference: tests read only the committed .npz files.
+"""
+from __future__ import annotations
+
+import asyncio
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get('AST_REFERENCE', '/root/reference')
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+VGG_SEED = 1234
+
+
+def import_reference():
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    import torch
+    import torchvision
+    with contextlib.redirect_stdout(io.StringIO()):
+        import neural_nets
+        import math_utils
+        import neural_style_transfer as nst
+
+    real_vgg19 = torchvision.models.vgg19  # neural_nets.models IS torchvision.models
+
+    def seeded_vgg19(pretrained=False, progress=False, **kw):
+        torch.manual_seed(VGG_SEED)
+        return real_vgg19(weights=None)
+
+    neural_nets.models.vgg19 = seeded_vgg19
+    return neural_nets, math_utils, nst
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def golden_small_ops(math_utils, nst):
+    import torch
+    import torch.nn.functional as F
+    import cv2
+    g = torch.Generator().manual_seed(0)
+    out = {}
+    # Gram (math_utils.py:26-34) on post-ReLU-like features
+    for name, shp in [('a', (1, 64, 8, 12)), ('b', (1, 128, 6, 8)), ('c', (2, 16, 5, 7))]:
+        x = torch.relu(torch.randn(shp, generator=g))
+        out[f'gram_x_{name}'] = x.numpy()
+        out[f'gram_g_{name}'] = math_utils.gram_matrix(x.clone()).numpy()
+        out[f'gram_gn_{name}'] = math_utils.gram_matrix(x.clone(), should_normalize=False).numpy()
+    # style MSE + autograd gradient through gram_matrix (nst.py:103)
+    x = torch.relu(torch.randn((1, 32, 6, 10), generator=g)).requires_grad_(True)
+    a = math_utils.gram_matrix(torch.relu(torch.randn((1, 32, 9, 9), generator=g)))
+    loss = torch.nn.MSELoss(reduction='mean')(a[0], math_utils.gram_matrix(x)[0])
+    loss.backward()
+    out['style_x'] = x.detach().numpy()
+    out['style_a'] = a.numpy()
+    out['style_loss'] = np.float64(loss.item())
+    out['style_grad'] = x.grad.numpy()
+    # total variation (math_utils.py:37-41)
+    y = (torch.randn((1, 3, 20, 30), generator=g) * 50).requires_grad_(True)
+    tv = math_utils.total_variation(y)
+    tv.backward()
+    out['tv_y'] = y.detach().numpy()
+    out['tv'] = np.float64(tv.item())
+    out['tv_grad'] = y.grad.numpy()
+    # in-loop pyramid (nst.py:173-176): exact 2x chain, and odd sizes
+    for name, shp in [('even', (1, 3, 64, 96)), ('odd', (1, 3, 50, 77))]:
+        p0 = (torch.randn(shp, generator=g) * 60).requires_grad_(True)
+        p1 = F.interpolate(p0, size=(shp[2] // 2, shp[3] // 2), mode='bicubic')
+        p2 = F.interpolate(p1, size=(p1.shape[2] // 2, p1.shape[3] // 2), mode='bicubic')
+        u1 = torch.randn(p1.shape, generator=g)
+        u2 = torch.randn(p2.shape, generator=g)
+        ((p1 * u1).sum() + (p2 * u2).sum()).backward()
+        out[f'pyr_{name}_p0'] = p0.detach().numpy()
+        out[f'pyr_{name}_p1'] = p1.detach().numpy()
+        out[f'pyr_{name}_p2'] = p2.detach().numpy()
+        out[f'pyr_{name}_u1'] = u1.numpy()
+        out[f'pyr_{name}_u2'] = u2.numpy()
+        out[f'pyr_{name}_grad'] = p0.grad.numpy()
+    # cv2 INTER_CUBIC (nst.py:226, :304, :427): up, down, via reference resize()
+    rng = np.random.default_rng(1)
+    low = rng.uniform(0, 1, size=(9, 13, 3)).astype(np.float32)
+    out['cv_up_in'] = low
+    out['cv_up_out'] = cv2.resize(low, dsize=(96, 64), interpolation=cv2.INTER_CUBIC)
+    big = rng.uniform(0, 1, size=(100, 150, 3)).astype(np.float32)
+    out['cv_down_in'] = big
+    out['cv_down_out'] = cv2.resize(big, dsize=(13, 9), interpolation=cv2.INTER_CUBIC)
+    odd = rng.uniform(0, 1, size=(60, 91, 3)).astype(np.float32)
+    out['resize_in'] = odd
+    r0 = asyncio.run(nst.resize(odd, 0))
+    out['resize_l0_shape'] = np.array(r0.shape)
+    out['resize_l0_sub'] = r0[::4, ::4].copy()
+    out['resize_l0_sum'] = np.float64(r0.astype(np.float64).sum())
+    # gaussian envelope (nst.py:396-418)
+    out['gmask'] = nst.gaussian_mask((40, 60, 3), 0.3, 0.2, 0.2)
+    # prepare / unprepare (nst.py:375-393)
+    img = rng.uniform(0, 1, size=(8, 12, 3)).astype(np.float32)
+    prep = nst.prepare_img(img, 'cpu')
+    out['prep_in'] = img
+    out['prep_out'] = prep.numpy()
+    out['unprep_out'] = nst.unprepare_img(prep.clone())
+    np.savez_compressed(os.path.join(OUT, 'small_ops.npz'), **out)
+    print('small_ops.npz', len(out), 'arrays')
+
+
+def capture_init(nst, content, style, **cfg):
+    """Run nst.neural_style_transfer with the optimizer stubbed; return the init image."""
+    captured = {}
+
+    class Stub:
+        def __init__(self, device, model_name, style_imgs, optimizer_name):
+            captured['style_levels'] = [s.shape for s in style_imgs]
+
+        async def process(self, content_imgs, init_img, *a, **k):
+            captured['init'] = np.array(init_img, copy=True)
+            captured['content_levels'] = [c.shape for c in content_imgs]
+            return
+            yield  # pragma: no cover
+
+    real = nst.NeuralStyleTransfer
+    nst.NeuralStyleTransfer = Stub
+    try:
+        async def run():
+            pair = nst.ContentStylePair(('c', content), ('s', style))
+            async for _ in nst.neural_style_transfer(pair, 1e3, 4e5, 1e2, 'lbfgs', 'vgg19',
+                                                     cfg['init_method'], 1, cfg['levels_num'],
+                                                     cfg['noise_factor'], cfg['noise_levels'],
+                                                     cfg['central'], cfg['peripheral'], cfg['dispersion']):
+                pass
+        quiet(asyncio.run, run())
+    finally:
+        nst.NeuralStyleTransfer = real
+    return captured
+
+
+def golden_noise_init(nst):
+    rng = np.random.default_rng(2)
+    content = rng.uniform(0, 1, size=(60, 90, 3)).astype(np.float32)
+    # smooth it a little so the Sobel map has structure
+    import cv2
+    content = np.clip(cv2.resize(cv2.resize(content, (12, 8), interpolation=cv2.INTER_CUBIC), (90, 60),
+                                 interpolation=cv2.INTER_CUBIC) * 0.7 + content * 0.3, 0, 1).astype(np.float32)
+    style = rng.uniform(0, 1, size=(50, 50, 3)).astype(np.float32)
+    default = dict(noise_factor=0.95, noise_levels=(9, 18, 36, -1, 0),
+                   central=(0.30, 0.20, 0.10, 0.20, 0.20), peripheral=(0.20, 0.30, 0.40, 0.10, 0.00),
+                   dispersion=(0.20, 0.30, 0.40, 0.60, 0.30))
+    pixel = dict(noise_factor=0.5, noise_levels=(-1,), central=(1.0,), peripheral=(1.0,), dispersion=(0.5,))
+    cases = {
+        'default_L1': dict(default, init_method='content+noise', levels_num=1, normal=False),
+        'default_L2': dict(default, init_method='content+noise', levels_num=2, normal=False),
+        'random_L1': dict(default, init_method='random', levels_num=1, normal=False),
+        'pixel_normal_L1': dict(pixel, init_method='content+noise', levels_num=1, normal=True),
+        'style_L1': dict(default, init_method='style', levels_num=1, normal=False),
+    }
+    out = {'content': content, 'style': style}
+    for name, cfg in cases.items():
+        nst.USE_NORMAL_NOISE_JUST_FOR_DEMONSTRATION = cfg['normal']
+        np.random.seed(0)
+        cap = capture_init(nst, content, style, **cfg)
+        init = cap['init']
+        step = 4 if cfg['levels_num'] == 1 else 8
+        out[f'{name}_shape'] = np.array(init.shape)
+        out[f'{name}_sub'] = init[::step, ::step].copy()
+        out[f'{name}_step'] = np.int64(step)
+        out[f'{name}_sum'] = np.float64(init.astype(np.float64).sum())
+        out[f'{name}_sumsq'] = np.float64((init.astype(np.float64) ** 2).sum())
+        out[f'{name}_dtype'] = np.array(str(init.dtype))
+        print(name, init.shape, init.dtype, float(init.mean()))
+    nst.USE_NORMAL_NOISE_JUST_FOR_DEMONSTRATION = False
+    np.savez_compressed(os.path.join(OUT, 'noise_init.npz'), **out)
+
+
+def golden_closure(math_utils, nst):
+    """LossBuilder.build (nst.py:84-112) + the closure's pyramid/sum/backward (nst.py:168-193),
+    driven through the reference's own classes on a 2-level 64x96 pyramid."""
+    import torch
+    import torch.nn.functional as F
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import gatys_oracle as O
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    net, cidx, sidx = quiet(math_utils.prepare_model, 'vgg19', 'cpu')
+    h, w = 64, 96
+    content, style = O.synthetic_images(h, w, seed=0)
+    rng = np.random.default_rng(3)
+    init = np.clip(content * 0.5 + rng.uniform(0, 1, size=content.shape) * 0.5, 0, 1).astype(np.float32)
+    import cv2
+    c_lv = [content, cv2.resize(content, (w // 2, h // 2), interpolation=cv2.INTER_CUBIC)]
+    s_lv = [style, cv2.resize(style, (w // 2, h // 2), interpolation=cv2.INTER_CUBIC)]
+    weights = (1e3, 4e5, 1e2)
+    builders = [quiet(nst.LossBuilder, cidx, sidx, nst.prepare_img(c, 'cpu'), nst.prepare_img(s, 'cpu'),
+                      net, *weights) for c, s in zip(c_lv, s_lv)]
+    out = {'content': content, 'style': style, 'init': init,
+           'content_l1': c_lv[1], 'style_l1': s_lv[1]}
+    for nlev in (1, 2):
+        img = nst.prepare_img(init, 'cpu').requires_grad_(True)
+        levels = [img]
+        total = None
+        per = []
+        for i in range(nlev):
+            if i > 0:
+                p = levels[i - 1]
+                levels.append(F.interpolate(p, size=(p.shape[2] // 2, p.shape[3] // 2), mode='bicubic'))
+            t, c, s, v = builders[i].build(levels[i])
+            per.append([t.item(), c.item(), s.item(), v.item()])
+            total = t if total is None else 1.0 * total + t
+        total.backward()
+        out[f'L{nlev}_per_level'] = np.array(per, dtype=np.float64)
+        out[f'L{nlev}_total'] = np.float64(total.item())
+        out[f'L{nlev}_grad'] = img.grad.numpy().copy()
+    # per-layer Grams of the top-level init image (Frobenius norms + the full 64x64 one)
+    with torch.no_grad():
+        feats = net(nst.prepare_img(init, 'cpu'))
+        grams = [math_utils.gram_matrix(feats[k].clone()) for k in sidx]
+    out['gram_fro'] = np.array([float(torch.linalg.norm(g)) for g in grams])
+    out['gram_relu1_1'] = grams[0].numpy()
+    out['gram_relu5_1_diag'] = torch.diagonal(grams[4][0]).numpy().copy()
+    np.savez_compressed(os.path.join(OUT, 'closure.npz'), **out)
+    print('closure.npz per-level', out['L2_per_level'])
+
+
+def golden_driver(nst):
+    """NeuralStyleTransfer.process (nst.py:123-208) end to end: Adam x4 and LBFGS x4 closures on
+    one 64x96 level; records the yielded images (subsampled) and step counters."""
+    import torch
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import gatys_oracle as O
+    content, style = O.synthetic_images(64, 96, seed=0)
+    rng = np.random.default_rng(3)
+    init = np.clip(content * 0.5 + rng.uniform(0, 1, size=content.shape) * 0.5, 0, 1).astype(np.float32)
+    out = {}
+    for opt, iters in (('adam', 4), ('lbfgs', 4)):
+        async def run():
+            drv = nst.NeuralStyleTransfer(torch.device('cpu'), 'vgg19', [style], opt)
+            res = []
+            async for img, step in drv.process([content], init, 10.0, iters, 1e3, 4e5, 1e2, 'golden'):
+                res.append((np.array(img, copy=True), step))
+            return res
+        res = quiet(asyncio.run, run())
+        torch.autograd.set_detect_anomaly(False)
+        out[f'{opt}_steps'] = np.array([s for _, s in res])
+        out[f'{opt}_final'] = res[-1][0]
+        out[f'{opt}_first'] = res[0][0]
+        print(opt, 'yields', [s for _, s in res], 'final mean', float(res[-1][0].mean()))
+    np.savez_compressed(os.path.join(OUT, 'driver.npz'), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    neural_nets, math_utils, nst = import_reference()
+    golden_small_ops(math_utils, nst)
+    golden_noise_init(nst)
+    golden_closure(math_utils, nst)
+    golden_driver(nst)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == '__main__':
+    main()
