@@ -1,0 +1,372 @@
+// Bicubic resampling kernels (Keys cubic, A = -0.75, per-tap index clamp, no antialias).
+//
+//   K4  bicubic_down2x      : the in-loop pyramid step, F.interpolate(x, (H/2, W/2), 'bicubic') at
+//                             neural_style_transfer.py:173-176 for even H, W.  src = 2d + 0.5 exactly, so the
+//                             taps are the constants [-3/32, 19/32, 19/32, -3/32] at rows/cols 2d-1..2d+2.
+//                             Input tile (+1/+2 halo) staged in shared memory from 16-byte global loads.
+//   K5  bicubic_down2x_adj  : its exact transpose in gather form (replaces the atomicAdd scatter of
+//                             upsample_bicubic2d_backward): each thread owns a 2x4 block of the input gradient
+//                             and reads the 3x4 output-gradient neighbourhood; deterministic.
+//   K6  bicubic_resize(_adj): arbitrary in/out sizes (odd pyramid levels, and cv2.resize(..., INTER_CUBIC) at
+//                             neural_style_transfer.py:226, :304, :427), CHW or HWC.
+//
+// All are HBM-bound: algorithmic traffic 4*C*(Hin*Win + Hout*Wout) bytes.
+#include "ast_common.cuh"
+
+namespace ast {
+
+__device__ __constant__ float kTap[4] = {-0.09375f, 0.59375f, 0.59375f, -0.09375f};
+
+// ---------------------------------------------------------------------------------------------------------
+// K4: exact 2x down.  Block = 256 threads, output tile 16 rows x 128 cols per plane.
+// Shared tile: 34 input rows x 258 input cols (cols 2*e0-1 .. 2*e0+256), local col = gcol - (2*e0-1) so that
+// every thread's first tap sits on an even (8-byte aligned) local column -> conflict-free LDS.64.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int D2_TH = 16, D2_TW = 128;
+constexpr int D2_SROWS = 2 * D2_TH + 2;        // 34 input rows
+constexpr int D2_HALF = D2_TW + 4;             // 132 entries per parity per row
+// Shared tile, split by column parity so that both the 16-byte global loads (stored as two 8-byte pairs) and
+// the per-output tap reads (stride-1 across the warp) are bank-conflict free:
+//   E[r][k+2] = x[row r][2*(e0+k)]      (even global columns), k = -2 .. 129
+//   O[r][k+1] = x[row r][2*(e0+k) - 1]  (odd  global columns), k = -1 .. 130
+// Output column e = e0+le reads O[le], E[le], O[le+1], E[le+1] = global columns 2e-1 .. 2e+2.
+
+__global__ void __launch_bounds__(256) down2x_kernel(const float* __restrict__ x, int H, int W,
+                                                    float* __restrict__ y, int vec_ok) {
+  __shared__ __align__(16) float tileE[D2_SROWS * D2_HALF];
+  __shared__ __align__(16) float tileO[D2_SROWS * D2_HALF];
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int e0 = blockIdx.x * D2_TW, d0 = blockIdx.y * D2_TH;
+  const float* xp = x + (size_t)blockIdx.z * H * W;
+  float* yp = y + (size_t)blockIdx.z * Ho * Wo;
+  const int gr0 = 2 * d0 - 1;  // global row of local row 0
+
+  if (vec_ok) {
+    // aligned float4 columns 2*e0-4 .. 2*e0+259 -> 66 float4 per row (W % 4 == 0, rows 16-byte aligned)
+    constexpr int V = 66;
+    for (int idx = threadIdx.x; idx < D2_SROWS * V; idx += 256) {
+      const int r = idx / V, v = idx - r * V;
+      const int gr = min(max(gr0 + r, 0), H - 1);
+      const int c4 = 2 * e0 - 4 + 4 * v;
+      const float* row = xp + (size_t)gr * W;
+      float4 val;
+      if (c4 < 0) {
+        const float e = __ldg(row);
+        val = make_float4(e, e, e, e);
+      } else if (c4 < W) {
+        val = ldg_stream(reinterpret_cast<const float4*>(row + c4));
+      } else {
+        const float e = __ldg(row + W - 1);
+        val = make_float4(e, e, e, e);
+      }
+      // columns c4, c4+2 are even -> E[2v-2 .. 2v-1] (+2); columns c4+1, c4+3 odd -> O[2v-1 .. 2v] (+1)
+      *reinterpret_cast<float2*>(tileE + r * D2_HALF + 2 * v) = make_float2(val.x, val.z);
+      *reinterpret_cast<float2*>(tileO + r * D2_HALF + 2 * v) = make_float2(val.y, val.w);
+    }
+  } else {
+    constexpr int SC = 2 * D2_TW + 2;  // local columns 0..257 <-> global 2*e0-1 .. 2*e0+256
+    for (int idx = threadIdx.x; idx < D2_SROWS * SC; idx += 256) {
+      const int r = idx / SC, c = idx - r * SC;
+      const int gr = min(max(gr0 + r, 0), H - 1);
+      const int gc = min(max(2 * e0 - 1 + c, 0), W - 1);
+      const float val = __ldg(xp + (size_t)gr * W + gc);
+      if ((c & 1) == 0) tileO[r * D2_HALF + (c >> 1) + 1] = val;   // unclamped column is odd
+      else              tileE[r * D2_HALF + (c >> 1) + 2] = val;   // unclamped column is even
+    }
+  }
+  __syncthreads();
+
+  // thread -> output column e0 + (tid % 128), 8 consecutive output rows starting at d0 + 8*(tid / 128)
+  const int le = threadIdx.x & (D2_TW - 1);
+  const int lr0 = (threadIdx.x >> 7) * 8;
+  const int e = e0 + le;
+  const float w0 = kTap[0], w1 = kTap[1];
+  float h[18];  // horizontally filtered local input rows 2*lr0 .. 2*lr0+17
+#pragma unroll
+  for (int r = 0; r < 18; ++r) {
+    const float* pe = tileE + (2 * lr0 + r) * D2_HALF + le + 2;
+    const float* po = tileO + (2 * lr0 + r) * D2_HALF + le + 1;
+    // same association as upsample_bicubic2d's cubic_interp1d: x0*c0 + x1*c1 + x2*c2 + x3*c3
+    h[r] = ((po[0] * w0 + pe[0] * w1) + po[1] * w1) + pe[1] * w0;
+  }
+  if (e < Wo) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int d = d0 + lr0 + k;
+      if (d < Ho) yp[(size_t)d * Wo + e] = ((h[2 * k] * w0 + h[2 * k + 1] * w1) + h[2 * k + 2] * w1) + h[2 * k + 3] * w0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: transpose of K4, gather form.  gx (C, H, W) with H = 2*Ho, W = 2*Wo; gy (C, Ho, Wo).
+// Per axis (m outputs, n = 2m inputs):
+//   out[2p]   = w1*g[p] + w3*g[p-1]   (+ w0*g[0]   folded from the clamped tap -1 when p == 0)
+//   out[2p+1] = w2*g[p] + w0*g[p+1]   (+ w3*g[m-1] folded from the clamped tap n  when p == m-1)
+// Thread = output-gradient row p, two output-gradient columns (q, q+1) -> writes 2 rows x float4 of gx.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adj_axis_weights(int p, int m, float& c_m1, float& c_0e, float& c_0o, float& c_p1) {
+  // contributions to (even, odd) input samples of position p from g[p-1], g[p], g[p+1]
+  c_m1 = (p >= 1) ? kTap[3] : 0.f;                       // even <- g[p-1]
+  c_0e = kTap[1] + ((p == 0) ? kTap[0] : 0.f);            // even <- g[p]
+  c_0o = kTap[2] + ((p == m - 1) ? kTap[3] : 0.f);        // odd  <- g[p]
+  c_p1 = (p + 1 <= m - 1) ? kTap[0] : 0.f;                // odd  <- g[p+1]
+}
+
+__global__ void __launch_bounds__(256) down2x_adj_kernel(const float* __restrict__ gy, int Ho, int Wo,
+                                                        float* __restrict__ gx, int accumulate, int vec_ok) {
+  const int W = 2 * Wo;
+  const int qpairs = (Wo + 1) >> 1;
+  const int64_t total = (int64_t)Ho * qpairs;
+  const float* gp = gy + (size_t)blockIdx.z * Ho * Wo;
+  float* xp = gx + (size_t)blockIdx.z * (2 * Ho) * W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(idx / qpairs);
+    const int q = 2 * (int)(idx - (int64_t)p * qpairs);
+    // vertical weights for rows 2p (even) and 2p+1 (odd)
+    float vy_m1, vy_0e, vy_0o, vy_p1;
+    adj_axis_weights(p, Ho, vy_m1, vy_0e, vy_0o, vy_p1);
+    // g columns q-1 .. q+2, vertically combined into even/odd input rows
+    float ge[4], go[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = q - 1 + k;
+      float a = 0.f, b = 0.f, d = 0.f;
+      if (c >= 0 && c < Wo) {
+        b = __ldg(gp + (size_t)p * Wo + c);
+        if (p >= 1) a = __ldg(gp + (size_t)(p - 1) * Wo + c);
+        if (p + 1 < Ho) d = __ldg(gp + (size_t)(p + 1) * Wo + c);
+      }
+      ge[k] = vy_m1 * a + vy_0e * b;
+      go[k] = vy_0o * b + vy_p1 * d;
+    }
+    float r0[4], r1[4];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {  // the two output-gradient columns q+s
+      float hx_m1, hx_0e, hx_0o, hx_p1;
+      adj_axis_weights(q + s, Wo, hx_m1, hx_0e, hx_0o, hx_p1);
+      r0[2 * s] = hx_m1 * ge[s] + hx_0e * ge[s + 1];
+      r0[2 * s + 1] = hx_0o * ge[s + 1] + hx_p1 * ge[s + 2];
+      r1[2 * s] = hx_m1 * go[s] + hx_0e * go[s + 1];
+      r1[2 * s + 1] = hx_0o * go[s + 1] + hx_p1 * go[s + 2];
+    }
+    float* o0 = xp + (size_t)(2 * p) * W + 2 * q;
+    float* o1 = o0 + W;
+    if (vec_ok && q + 1 < Wo) {
+      float4 a = make_float4(r0[0], r0[1], r0[2], r0[3]);
+      float4 b = make_float4(r1[0], r1[1], r1[2], r1[3]);
+      if (accumulate) {
+        const float4 pa = *reinterpret_cast<const float4*>(o0), pb = *reinterpret_cast<const float4*>(o1);
+        a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+        b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+      }
+      *reinterpret_cast<float4*>(o0) = a;
+      *reinterpret_cast<float4*>(o1) = b;
+    } else {
+      const int ncol = (q + 1 < Wo) ? 4 : 2;
+      for (int k = 0; k < ncol; ++k) {
+        o0[k] = accumulate ? o0[k] + r0[k] : r0[k];
+        o1[k] = accumulate ? o1[k] + r1[k] : r1[k];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K6: general-ratio bicubic gather.
+// ---------------------------------------------------------------------------------------------------------
+struct AxisMap {
+  float scale_f;    // torch: (float)in / out
+  double scale_d;   // cv2 : 1.0 / ((double)out / in)
+};
+
+__host__ __device__ inline AxisMap make_axis(int n_in, int n_out) {
+  AxisMap a;
+  a.scale_f = (float)n_in / (float)n_out;
+  a.scale_d = 1.0 / ((double)n_out / (double)n_in);
+  return a;
+}
+
+__device__ __forceinline__ void src_index(const AxisMap& a, int d, int coord_mode, int& ix, float& t) {
+  float src;
+  if (coord_mode == AST_COORD_TORCH) {
+    src = a.scale_f * ((float)d + 0.5f) - 0.5f;   // area_pixel_compute_source_index (cubic: no clamp at 0)
+  } else {
+    src = (float)(((double)d + 0.5) * a.scale_d - 0.5);  // cv2 resizeGeneric: fx = (float)((dx+0.5)*scale - 0.5)
+  }
+  const float fl = floorf(src);
+  ix = (int)fl;
+  t = src - fl;
+}
+
+__device__ __forceinline__ void cubic_coeffs(float t, int coord_mode, float w[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.0f;
+  w[0] = ((A * x0 - 5.0f * A) * x0 + 8.0f * A) * x0 - 4.0f * A;
+  w[1] = ((A + 2.0f) * t - (A + 3.0f)) * t * t + 1.0f;
+  const float u = 1.0f - t;
+  w[2] = ((A + 2.0f) * u - (A + 3.0f)) * u * u + 1.0f;
+  if (coord_mode == AST_COORD_TORCH) {
+    const float x3 = u + 1.0f;
+    w[3] = ((A * x3 - 5.0f * A) * x3 + 8.0f * A) * x3 - 4.0f * A;   // get_cubic_upsample_coefficients
+  } else {
+    w[3] = 1.0f - w[0] - w[1] - w[2];                               // cv2 interpolateCubic
+  }
+}
+
+// One thread per output pixel (x fastest).  CHW: plane = blockIdx.z.  HWC: thread loops the C channels.
+__global__ void __launch_bounds__(256) resize_kernel(const float* __restrict__ x, int C, int Hin, int Win,
+                                                    float* __restrict__ y, int Hout, int Wout, int layout,
+                                                    int coord_mode, AxisMap ay, AxisMap ax) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y;
+  if (ox >= Wout) return;
+  int iy, ixx;
+  float ty, tx;
+  src_index(ay, oy, coord_mode, iy, ty);
+  src_index(ax, ox, coord_mode, ixx, tx);
+  float wy[4], wx[4];
+  cubic_coeffs(ty, coord_mode, wy);
+  cubic_coeffs(tx, coord_mode, wx);
+  int ry[4], rx[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    ry[k] = min(max(iy - 1 + k, 0), Hin - 1);
+    rx[k] = min(max(ixx - 1 + k, 0), Win - 1);
+  }
+  if (layout == AST_LAYOUT_CHW) {
+    const float* xp = x + (size_t)blockIdx.z * Hin * Win;
+    float acc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float* row = xp + (size_t)ry[i] * Win;
+      acc[i] = ((__ldg(row + rx[0]) * wx[0] + __ldg(row + rx[1]) * wx[1]) + __ldg(row + rx[2]) * wx[2]) +
+               __ldg(row + rx[3]) * wx[3];
+    }
+    y[((size_t)blockIdx.z * Hout + oy) * Wout + ox] = ((acc[0] * wy[0] + acc[1] * wy[1]) + acc[2] * wy[2]) + acc[3] * wy[3];
+  } else {
+    for (int c = 0; c < C; ++c) {
+      float acc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float* row = x + (size_t)ry[i] * Win * C + c;
+        acc[i] = ((__ldg(row + (size_t)rx[0] * C) * wx[0] + __ldg(row + (size_t)rx[1] * C) * wx[1]) +
+                  __ldg(row + (size_t)rx[2] * C) * wx[2]) + __ldg(row + (size_t)rx[3] * C) * wx[3];
+      }
+      y[((size_t)oy * Wout + ox) * C + c] = ((acc[0] * wy[0] + acc[1] * wy[1]) + acc[2] * wy[2]) + acc[3] * wy[3];
+    }
+  }
+}
+
+// Weight with which output sample d touches input sample i along one axis (sum over clamped taps).
+__device__ __forceinline__ float axis_weight(const AxisMap& a, int d, int i, int n_in, int coord_mode) {
+  int ix;
+  float t;
+  src_index(a, d, coord_mode, ix, t);
+  float w[4];
+  cubic_coeffs(t, coord_mode, w);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (min(max(ix - 1 + k, 0), n_in - 1) == i) s += w[k];
+  return s;
+}
+
+__device__ __forceinline__ void adj_range(int i, int n_in, int n_out, int& lo, int& hi) {
+  // conservative range of output samples whose (clamped) 4 taps can reach input sample i
+  const double inv = (double)n_out / (double)n_in;
+  lo = (int)floor(((double)i - 2.0 + 0.5) * inv - 0.5) - 1;
+  hi = (int)ceil(((double)i + 2.0 + 0.5) * inv - 0.5) + 1;
+  if (i == 0) lo = 0;
+  if (i == n_in - 1) hi = n_out - 1;
+  lo = max(lo, 0);
+  hi = min(hi, n_out - 1);
+}
+
+// Transpose of resize_kernel (CHW) in gather form: one thread per INPUT pixel.
+__global__ void __launch_bounds__(256) resize_adj_kernel(const float* __restrict__ gy, int Hin, int Win, int Hout,
+                                                        int Wout, float* __restrict__ gx, int accumulate,
+                                                        int coord_mode, AxisMap ay, AxisMap ax) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= Win) return;
+  int dlo, dhi, elo, ehi;
+  adj_range(i, Hin, Hout, dlo, dhi);
+  adj_range(j, Win, Wout, elo, ehi);
+  const float* gp = gy + (size_t)blockIdx.z * Hout * Wout;
+  float acc = 0.f;
+  for (int d = dlo; d <= dhi; ++d) {
+    const float wy = axis_weight(ay, d, i, Hin, coord_mode);
+    if (wy == 0.f) continue;
+    float rowacc = 0.f;
+    for (int e = elo; e <= ehi; ++e) {
+      const float wx = axis_weight(ax, e, j, Win, coord_mode);
+      if (wx != 0.f) rowacc += wx * __ldg(gp + (size_t)d * Wout + e);
+    }
+    acc += wy * rowacc;
+  }
+  float* o = gx + ((size_t)blockIdx.z * Hin + i) * Win + j;
+  *o = accumulate ? *o + acc : acc;
+}
+
+}  // namespace ast
+
+using namespace ast;
+
+static inline bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" int ast_bicubic_down2x(const float* x, int C, int H, int W, float* y, void* stream) {
+  AST_REQUIRE(x && y, AST_ERR_INVALID, "ast_bicubic_down2x: null pointer");
+  AST_REQUIRE(C > 0 && H >= 2 && W >= 2, AST_ERR_INVALID, "ast_bicubic_down2x: bad shape %dx%dx%d", C, H, W);
+  AST_REQUIRE((H % 2 == 0) && (W % 2 == 0), AST_ERR_UNSUPPORTED,
+              "ast_bicubic_down2x: H and W must be even (got %dx%d); use ast_bicubic_resize", H, W);
+  AST_REQUIRE(C <= 65535, AST_ERR_INVALID, "ast_bicubic_down2x: too many planes");
+  const int Ho = H / 2, Wo = W / 2;
+  const int vec_ok = aligned16p(x) && (W % 4 == 0);
+  dim3 grid((Wo + D2_TW - 1) / D2_TW, (Ho + D2_TH - 1) / D2_TH, C);
+  down2x_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, H, W, y, vec_ok);
+  return check_launch("ast_bicubic_down2x");
+}
+
+extern "C" int ast_bicubic_down2x_adj(const float* gy, int C, int H, int W, float* gx, int accumulate,
+                                      void* stream) {
+  AST_REQUIRE(gy && gx, AST_ERR_INVALID, "ast_bicubic_down2x_adj: null pointer");
+  AST_REQUIRE(C > 0 && H >= 2 && W >= 2, AST_ERR_INVALID, "ast_bicubic_down2x_adj: bad shape %dx%dx%d", C, H, W);
+  AST_REQUIRE((H % 2 == 0) && (W % 2 == 0), AST_ERR_UNSUPPORTED,
+              "ast_bicubic_down2x_adj: H and W must be even (got %dx%d); use ast_bicubic_resize_adj", H, W);
+  AST_REQUIRE(C <= 65535, AST_ERR_INVALID, "ast_bicubic_down2x_adj: too many planes");
+  const int Ho = H / 2, Wo = W / 2;
+  const int vec_ok = aligned16p(gx) && (W % 4 == 0);
+  const int64_t total = (int64_t)Ho * ((Wo + 1) / 2);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dim3 grid((unsigned)blocks, 1, C);
+  down2x_adj_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gy, Ho, Wo, gx, accumulate, vec_ok);
+  return check_launch("ast_bicubic_down2x_adj");
+}
+
+extern "C" int ast_bicubic_resize(const float* x, int C, int Hin, int Win, float* y, int Hout, int Wout, int layout,
+                                  int coord_mode, void* stream) {
+  AST_REQUIRE(x && y, AST_ERR_INVALID, "ast_bicubic_resize: null pointer");
+  AST_REQUIRE(C > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, AST_ERR_INVALID, "ast_bicubic_resize: bad shape");
+  AST_REQUIRE(layout == AST_LAYOUT_CHW || layout == AST_LAYOUT_HWC, AST_ERR_INVALID, "ast_bicubic_resize: bad layout %d", layout);
+  AST_REQUIRE(coord_mode == AST_COORD_TORCH || coord_mode == AST_COORD_CV2, AST_ERR_INVALID, "ast_bicubic_resize: bad coord_mode %d", coord_mode);
+  AST_REQUIRE(Hout <= 65535 && C <= 65535, AST_ERR_UNSUPPORTED, "ast_bicubic_resize: Hout/C exceed grid limits");
+  dim3 grid((Wout + 255) / 256, Hout, layout == AST_LAYOUT_CHW ? C : 1);
+  resize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, C, Hin, Win, y, Hout, Wout, layout, coord_mode,
+                                                        make_axis(Hin, Hout), make_axis(Win, Wout));
+  return check_launch("ast_bicubic_resize");
+}
+
+extern "C" int ast_bicubic_resize_adj(const float* gy, int C, int Hin, int Win, int Hout, int Wout, float* gx,
+                                      int accumulate, int coord_mode, void* stream) {
+  AST_REQUIRE(gy && gx, AST_ERR_INVALID, "ast_bicubic_resize_adj: null pointer");
+  AST_REQUIRE(C > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, AST_ERR_INVALID, "ast_bicubic_resize_adj: bad shape");
+  AST_REQUIRE(coord_mode == AST_COORD_TORCH || coord_mode == AST_COORD_CV2, AST_ERR_INVALID, "ast_bicubic_resize_adj: bad coord_mode %d", coord_mode);
+  AST_REQUIRE(Hin <= 65535 && C <= 65535, AST_ERR_UNSUPPORTED, "ast_bicubic_resize_adj: Hin/C exceed grid limits");
+  dim3 grid((Win + 255) / 256, Hin, C);
+  resize_adj_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gy, Hin, Win, Hout, Wout, gx, accumulate, coord_mode,
+                                                            make_axis(Hin, Hout), make_axis(Win, Wout));
+  return check_launch("ast_bicubic_resize_adj");
+}

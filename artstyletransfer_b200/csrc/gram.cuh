@@ -1,0 +1,39 @@
+// Internal interface between the Gram entry points (gram.cu), the exact-fp32 FFMA kernels (gram.cu) and the
+// tcgen05 kernels (gram_tc.cu).
+#pragma once
+
+#include "ast_common.cuh"
+
+namespace ast {
+
+constexpr int kGramMaxTiles = 3;
+
+// How the split-K partial sums of F F^T are laid out in the workspace, for the finalize kernel.
+// The C x C output is cut into (C/TR)^2 square tiles of TR x TR; only tiles with bi <= bj are stored
+// (the Gram is symmetric); tile t has part_cnt[t] partial sums, partial p at
+//   partials + (part_off[t] + p) * TR * TR   (row-major TR x TR fp32).
+struct GramPlan {
+  int C;
+  int TR;
+  int n_tiles;
+  int tile_bi[kGramMaxTiles], tile_bj[kGramMaxTiles];
+  int part_off[kGramMaxTiles], part_cnt[kGramMaxTiles];
+  int total_parts;
+};
+
+constexpr size_t kGramWsHeaderBytes = 32768;  // ReduceWs (ticket + per-block loss partials) lives here
+
+static_assert(sizeof(ReduceWs) <= kGramWsHeaderBytes, "reduce header too small");
+
+// gram_tc.cu -------------------------------------------------------------------------------------------
+// True when the tcgen05 path handles this problem: C in {64,128,256,512}, HW % 4 == 0 (TMA row pitch is a
+// multiple of 16 bytes) and a 16-byte aligned base pointer.
+bool gram_tc_supported(int C, int64_t HW, const void* F);
+// Plans the split-K decomposition for `num_sms` SMs (no device access).
+void gram_tc_plan(int C, int64_t HW, int num_sms, GramPlan* plan);
+int gram_tc_fwd(const float* F, int C, int64_t HW, float* partials, const GramPlan& plan, int num_sms,
+                cudaStream_t stream);
+int gram_tc_bwd(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale, float* dF,
+                int accumulate, int num_sms, cudaStream_t stream);
+
+}  // namespace ast

@@ -1,0 +1,574 @@
+// tcgen05 / TMEM / TMA Gram kernels for sm_100a (AST_PREC_TF32).
+//
+// Forward  (K1): G_partial = F[:, ks] F[:, ks]^T.  F is (C, HW) row-major, i.e. K-major for BOTH operands, so a
+//   CTA TMA-loads ONE slab of rows x 32 fp32 (128-byte swizzle atom) per K chunk and points both UMMA
+//   descriptors at it.  Split-K over the CTAs (one CTA per SM); accumulators live in TMEM; each CTA writes its
+//   partial tile to the workspace and gram_finalize_kernel (gram.cu) reduces them in a fixed order.
+// Backward (K2): dF = s * D F, computed transposed, dF^T[n, c] = sum_k F[k, n] D[c, k]:  A = F tile as an
+//   MN-major operand (M = 128 spatial positions, contiguous), B = D (K-major), accumulator lane = spatial
+//   position so the epilogue's global loads/stores are 128-byte coalesced.  D stays resident in shared memory
+//   for C <= 128 and is streamed from L2 per K chunk for C >= 256.
+//
+// Operands are fp32 in HBM.  tcgen05 kind::tf32 reads fp32 bit patterns and TRUNCATES the low 13 mantissa bits,
+// which biases a Gram of non-negative (post-ReLU) features by ~1e-3 relative.  A converter warpgroup therefore
+// rounds each staged tile to nearest TF32 in place (cvt.rna.tf32.f32) between the TMA landing and the MMA.
+//
+// Pipeline per stage:  TMA (warp 0) --full--> converters (4 warps) --conv--> MMA (warp 1) --empty--> TMA
+// and                  MMA --acc_full--> epilogue warps (tcgen05.ld) [--acc_empty--> MMA in the backward].
+#include "gram.cuh"
+#include "sm100_ptx.cuh"
+
+namespace ast {
+
+using namespace ptx;
+
+constexpr int BK = 32;                 // fp32 elements per 128-byte swizzle row
+constexpr int ROW_BYTES = BK * 4;      // 128
+
+// ------------------------------------------------------------------------------------------------------
+// host: tensor maps
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;   // resolved once; pure function of the driver
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major (rows, cols) tensor, box = (box_rows x 32 cols), 128-byte swizzle, zero OOB fill.
+static int make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return AST_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu box_rows=%u", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    return AST_ERR_CUDA;
+  }
+  return AST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// shared device pieces
+// ------------------------------------------------------------------------------------------------------
+// Round `bytes` of staged fp32 to nearest TF32 in place; 128 converter threads, 16 B per access.
+__device__ __forceinline__ void convert_tf32_inplace(uint8_t* base, int bytes, int ctid) {
+  float4* p = reinterpret_cast<float4*>(base);
+  const int n = bytes >> 4;
+#pragma unroll 4
+  for (int i = ctid; i < n; i += 128) {
+    float4 v = p[i];
+    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+    p[i] = v;
+  }
+}
+
+struct FwdParams {
+  int64_t HW;
+  int n_tiles;
+  int cta_off[kGramMaxTiles + 1];   // CTAs of tile t: [cta_off[t], cta_off[t+1])
+  int tile_bi[kGramMaxTiles], tile_bj[kGramMaxTiles];
+  int part_off[kGramMaxTiles];
+  int units_total;                  // K units (stage fills) covering HW
+  float* partials;
+};
+
+template <int C>
+struct FwdCfg {
+  static constexpr int kUnitChunks = (C == 64) ? 2 : 1;               // 32-wide K chunks per stage
+  static constexpr int kBoxRows = (C == 64) ? 64 : (C == 128 ? 128 : 256);
+  static constexpr int kStageBytes = (C == 512) ? 65536 : (C == 256 ? 32768 : 16384);
+  static constexpr int kStages = (C == 512) ? 3 : (C == 256 ? 6 : 8);
+  static constexpr int kTmemCols = (C <= 128) ? 128 : 512;
+  static constexpr int kTR = (C <= 256) ? C : 256;                     // partial tile edge
+  static constexpr int kUmmaN = (C <= 128) ? 128 : 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: converters then epilogue.
+template <int C>
+__global__ void __launch_bounds__(192, 1) gram_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                            const __grid_constant__ FwdParams P) {
+  using Cfg = FwdCfg<C>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  // bars[0..S) full, [S..2S) conv, [2S..3S) empty, [3S] acc_full ; then tmem slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
+  const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + S), bar_empty = smem_u32(bars + 2 * S),
+                 bar_acc = smem_u32(bars + 3 * S);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // which tile / split am I?
+  int t = 0;
+  while (t + 1 < P.n_tiles && (int)blockIdx.x >= P.cta_off[t + 1]) ++t;
+  const int split = blockIdx.x - P.cta_off[t];
+  const int nsplit = P.cta_off[t + 1] - P.cta_off[t];
+  const int base_u = P.units_total / nsplit, rem_u = P.units_total % nsplit;
+  const int u_begin = split * base_u + min(split, rem_u);
+  const int n_units = base_u + (split < rem_u ? 1 : 0);
+  const bool offdiag = (C == 512) && (P.tile_bi[t] != P.tile_bj[t]);
+  const int stage_tx_bytes = (C == 512) ? (offdiag ? 65536 : 32768) : Cfg::kStageBytes;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, 128);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int i = 0; i < n_units; ++i) {
+        const int s = i % S;
+        const uint32_t ph = (uint32_t)(i / S) & 1u;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)stage_tx_bytes);
+        const uint32_t dst = smem_u32(smem + s * Cfg::kStageBytes);
+        const int u = u_begin + i;
+        if (C == 64) {
+          tma_load_2d(dst, &tmap, bar_full + 8 * s, (2 * u) * BK, 0);
+          tma_load_2d(dst + 64 * ROW_BYTES, &tmap, bar_full + 8 * s, (2 * u + 1) * BK, 0);
+        } else if (C <= 256) {
+          tma_load_2d(dst, &tmap, bar_full + 8 * s, u * BK, 0);
+        } else {
+          tma_load_2d(dst, &tmap, bar_full + 8 * s, u * BK, P.tile_bi[t] * 256);
+          if (offdiag) tma_load_2d(dst + 256 * ROW_BYTES, &tmap, bar_full + 8 * s, u * BK, P.tile_bj[t] * 256);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_tf32(128, Cfg::kUmmaN, 0, 0);
+      for (int i = 0; i < n_units; ++i) {
+        const int s = i % S;
+        const uint32_t ph = (uint32_t)(i / S) & 1u;
+        mbar_wait(bar_conv + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint32_t b_base = offdiag ? a_base + 256 * ROW_BYTES : a_base;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+          const uint64_t bd = umma_desc_sw128(b_base + k * 32, 16, 1024);
+          if (C <= 128) {
+            umma_tf32(tmem_base, umma_desc_sw128(a_base + k * 32, 16, 1024), bd, idesc, acc);
+          } else {
+            umma_tf32(tmem_base, umma_desc_sw128(a_base + k * 32, 16, 1024), bd, idesc, acc);
+            umma_tf32(tmem_base + 256, umma_desc_sw128(a_base + 128 * ROW_BYTES + k * 32, 16, 1024), bd, idesc, acc);
+          }
+        }
+        umma_commit(bar_empty + 8 * s);
+      }
+      umma_commit(bar_acc);
+    }
+  } else {
+    // ===== converters (128 threads), then epilogue =====
+    const int ctid = threadIdx.x - 64;
+    for (int i = 0; i < n_units; ++i) {
+      const int s = i % S;
+      const uint32_t ph = (uint32_t)(i / S) & 1u;
+      mbar_wait(bar_full + 8 * s, ph);
+      convert_tf32_inplace(smem + s * Cfg::kStageBytes, stage_tx_bytes, ctid);
+      fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(bar_conv + 8 * s);
+    }
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int sub = warp & 3;            // TMEM sub-partition this warp may read
+    const int row = sub * 32 + lane;     // accumulator lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(sub * 32) << 16);
+    constexpr int TR = Cfg::kTR;
+    uint32_t v[32];
+    if (C == 64) {
+      // stacked units: rows 0..63 x cols 0..63 and rows 64..127 x cols 64..127 are two partial Grams
+      const int half = row >> 6;
+      float* dst = P.partials + ((size_t)(P.part_off[t] + 2 * split + half) * TR + (row & 63)) * TR;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        tmem_ld_x32(lane_addr + half * 64 + g * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          reinterpret_cast<float4*>(dst + g * 32)[q] =
+              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                          __uint_as_float(v[4 * q + 3]));
+      }
+    } else {
+      constexpr int kRowBlocks = (C == 128) ? 1 : 2;
+      constexpr int kCols = (C == 128) ? 128 : 256;
+      float* tile = P.partials + (size_t)(P.part_off[t] + split) * TR * TR;
+#pragma unroll 1
+      for (int rb = 0; rb < kRowBlocks; ++rb) {
+        float* dst = tile + (size_t)(rb * 128 + row) * TR;
+#pragma unroll 1
+        for (int g = 0; g < kCols / 32; ++g) {
+          tmem_ld_x32(lane_addr + rb * 256 + g * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            reinterpret_cast<float4*>(dst + g * 32)[q] =
+                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                            __uint_as_float(v[4 * q + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------
+struct BwdParams {
+  int64_t HW;
+  int n_tiles;       // ceil(HW / 128)
+  float scale;
+  const float* gscale;   // nullable device scalar multiplied into scale
+  int accumulate;
+  float* dF;
+};
+
+template <int C>
+struct BwdCfg {
+  static constexpr bool kResidentD = (C <= 128);
+  static constexpr int kFBytes = 128 * BK * 4;                          // 16 KB: 32 channels x 128 positions
+  static constexpr int kDChunkBytes = C * ROW_BYTES;                    // C rows x 32 k
+  static constexpr int kStageBytes = kFBytes + (kResidentD ? 0 : kDChunkBytes);
+  static constexpr int kStages = (C == 512) ? 2 : (C == 256 ? 4 : 6);
+  static constexpr int kDResBytes = kResidentD ? C * C * 4 : 0;
+  static constexpr int kAccBufs = (C == 512) ? 1 : 2;
+  static constexpr int kTmemCols = (C == 64) ? 128 : (C == 128 ? 256 : 512);
+  static constexpr int kUmmaN = (C <= 256) ? C : 256;
+  static constexpr int kDBoxRows = (C <= 256) ? C : 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kDResBytes + 1024 + 256;
+};
+
+// warp 0: TMA, warp 1: MMA + TMEM, warps 2..5: converters, warps 6..9: epilogue.
+template <int C>
+__global__ void __launch_bounds__(320, 1) gram_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmapF,
+                                                            const __grid_constant__ CUtensorMap tmapD,
+                                                            const __grid_constant__ BwdParams P) {
+  using Cfg = BwdCfg<C>;
+  constexpr int S = Cfg::kStages;
+  constexpr int KC = C / BK;            // K chunks per tile
+  constexpr int NB = Cfg::kAccBufs;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* dres = smem + S * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dres + Cfg::kDResBytes);
+  // full[S] conv[S] empty[S] acc_full[2] acc_empty[2] d_full d_conv
+  const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + S), bar_empty = smem_u32(bars + 2 * S),
+                 bar_accf = smem_u32(bars + 3 * S), bar_acce = smem_u32(bars + 3 * S + 2),
+                 bar_dfull = smem_u32(bars + 3 * S + 4), bar_dconv = smem_u32(bars + 3 * S + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 6);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_tiles = ((int)blockIdx.x < P.n_tiles) ? (P.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmapF);
+    prefetch_tmap(&tmapD);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, 128);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_accf + 8 * b, 1);
+      mbar_init(bar_acce + 8 * b, 128);
+    }
+    mbar_init(bar_dfull, 1);
+    mbar_init(bar_dconv, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      if (Cfg::kResidentD) {
+        mbar_arrive_expect_tx(bar_dfull, (uint32_t)Cfg::kDResBytes);
+        for (int kc = 0; kc < KC; ++kc)
+          tma_load_2d(smem_u32(dres + kc * Cfg::kDChunkBytes), &tmapD, bar_dfull, kc * BK, 0);
+      }
+      int it = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int64_t n0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * 128;
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)Cfg::kStageBytes);
+          const uint32_t dst = smem_u32(smem + s * Cfg::kStageBytes);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)   // four 32-position strips, 32 channel rows each (4 KB)
+            tma_load_2d(dst + j * 4096, &tmapF, bar_full + 8 * s, (int)(n0 + 32 * j), kc * BK);
+          if (!Cfg::kResidentD) {
+            tma_load_2d(dst + Cfg::kFBytes, &tmapD, bar_full + 8 * s, kc * BK, 0);
+            if (C == 512) tma_load_2d(dst + Cfg::kFBytes + 256 * ROW_BYTES, &tmapD, bar_full + 8 * s, kc * BK, 256);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_tf32(128, Cfg::kUmmaN, /*A MN-major*/ 1, /*B K-major*/ 0);
+      if (Cfg::kResidentD) {
+        mbar_wait(bar_dconv, 0);
+        tc_fence_after();
+      }
+      int it = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int b = ti % NB;
+        const uint32_t bph = (uint32_t)(ti / NB) & 1u;
+        mbar_wait(bar_acce + 8 * b, bph ^ 1u);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + b * C;
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(bar_conv + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t f_base = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t d_base = Cfg::kResidentD ? smem_u32(dres + kc * Cfg::kDChunkBytes) : f_base + Cfg::kFBytes;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint32_t acc = (kc > 0 || k > 0) ? 1u : 0u;
+            // A: 8 channel rows (1024 B) per K step; 32-position strips 4096 B apart (LBO)
+            const uint64_t ad = umma_desc_sw128(f_base + k * 1024, 4096, 1024);
+            umma_tf32(d_tmem, ad, umma_desc_sw128(d_base + k * 32, 16, 1024), idesc, acc);
+            if (C == 512)
+              umma_tf32(d_tmem + 256, ad, umma_desc_sw128(d_base + 256 * ROW_BYTES + k * 32, 16, 1024), idesc, acc);
+          }
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_accf + 8 * b);
+      }
+    }
+  } else if (warp < 6) {
+    // ===== converters =====
+    const int ctid = threadIdx.x - 64;
+    if (Cfg::kResidentD) {
+      mbar_wait(bar_dfull, 0);
+      convert_tf32_inplace(dres, Cfg::kDResBytes, ctid);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_dconv);
+    }
+    const int total = my_tiles * KC;
+    for (int it = 0; it < total; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (uint32_t)(it / S) & 1u;
+      mbar_wait(bar_full + 8 * s, ph);
+      convert_tf32_inplace(smem + s * Cfg::kStageBytes, Cfg::kStageBytes, ctid);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_conv + 8 * s);
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> (+=) global, 128-byte coalesced per channel =====
+    const int sub = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(sub * 32) << 16);
+    const float scale = P.gscale ? P.scale * __ldg(P.gscale) : P.scale;
+    uint32_t v[32];
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int b = ti % NB;
+      const uint32_t bph = (uint32_t)(ti / NB) & 1u;
+      const int64_t n = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * 128 + sub * 32 + lane;
+      mbar_wait(bar_accf + 8 * b, bph);
+      tc_fence_after();
+      float* out = P.dF + n;
+#pragma unroll 1
+      for (int g = 0; g < C / 32; ++g) {
+        tmem_ld_x32(lane_addr + b * C + g * 32, v);
+        tmem_ld_wait();
+        if (n < P.HW) {
+          float* o = out + (size_t)(g * 32) * P.HW;
+          if (P.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[(size_t)j * P.HW] += scale * __uint_as_float(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[(size_t)j * P.HW] = scale * __uint_as_float(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acce + 8 * b);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+bool gram_tc_supported(int C, int64_t HW, const void* F) {
+  if (!(C == 64 || C == 128 || C == 256 || C == 512)) return false;
+  if (HW <= 0 || (HW % 4) != 0 || HW > (int64_t)0x7fffff00) return false;
+  if (F && (reinterpret_cast<uintptr_t>(F) & 15u)) return false;
+  return true;
+}
+
+void gram_tc_plan(int C, int64_t HW, int num_sms, GramPlan* plan) {
+  const int64_t chunks = (HW + BK - 1) / BK;
+  const int64_t units = (C == 64) ? (chunks + 1) / 2 : chunks;
+  const int min_units = 4;   // do not split finer than 4 stage fills per CTA
+  plan->C = C;
+  plan->TR = (C <= 256) ? C : 256;
+  if (C <= 256) {
+    int64_t ns = units / min_units;
+    if (ns > num_sms) ns = num_sms;
+    if (ns < 1) ns = 1;
+    plan->n_tiles = 1;
+    plan->tile_bi[0] = plan->tile_bj[0] = 0;
+    plan->part_off[0] = 0;
+    plan->part_cnt[0] = (int)ns * (C == 64 ? 2 : 1);
+    plan->total_parts = plan->part_cnt[0];
+  } else {
+    // three 256x256 tiles (0,0) (0,1) (1,1); the off-diagonal one loads twice the bytes per unit -> 2x the CTAs
+    int64_t sd = num_sms / 4;
+    if (sd > units / min_units) sd = units / min_units;
+    if (sd < 1) sd = 1;
+    int64_t so = 2 * sd;
+    if (so > units) so = units;
+    plan->n_tiles = 3;
+    const int bi[3] = {0, 0, 1}, bj[3] = {0, 1, 1};
+    const int cnt[3] = {(int)sd, (int)so, (int)sd};
+    int off = 0;
+    for (int t = 0; t < 3; ++t) {
+      plan->tile_bi[t] = bi[t];
+      plan->tile_bj[t] = bj[t];
+      plan->part_off[t] = off;
+      plan->part_cnt[t] = cnt[t];
+      off += cnt[t];
+    }
+    plan->total_parts = off;
+  }
+}
+
+template <int C>
+static int launch_fwd(const float* F, int64_t HW, float* partials, const GramPlan& plan, cudaStream_t stream) {
+  using Cfg = FwdCfg<C>;
+  CUtensorMap tmap;
+  int rc = make_tmap(&tmap, F, C, HW, Cfg::kBoxRows);
+  if (rc != AST_OK) return rc;
+  FwdParams P;
+  P.HW = HW;
+  P.n_tiles = plan.n_tiles;
+  const int64_t chunks = (HW + BK - 1) / BK;
+  P.units_total = (int)((C == 64) ? (chunks + 1) / 2 : chunks);
+  int off = 0;
+  for (int t = 0; t < plan.n_tiles; ++t) {
+    P.cta_off[t] = off;
+    P.tile_bi[t] = plan.tile_bi[t];
+    P.tile_bj[t] = plan.tile_bj[t];
+    P.part_off[t] = plan.part_off[t];
+    off += (C == 64) ? plan.part_cnt[t] / 2 : plan.part_cnt[t];
+  }
+  P.cta_off[plan.n_tiles] = off;
+  P.partials = partials;
+  cudaError_t e = cudaFuncSetAttribute(gram_fwd_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (e != cudaSuccess) {
+    set_error("gram_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return AST_ERR_CUDA;
+  }
+  gram_fwd_tc_kernel<C><<<off, 192, Cfg::kSmemBytes, stream>>>(tmap, P);
+  return check_launch("gram_fwd_tc");
+}
+
+int gram_tc_fwd(const float* F, int C, int64_t HW, float* partials, const GramPlan& plan, int num_sms,
+                cudaStream_t stream) {
+  (void)num_sms;
+  switch (C) {
+    case 64: return launch_fwd<64>(F, HW, partials, plan, stream);
+    case 128: return launch_fwd<128>(F, HW, partials, plan, stream);
+    case 256: return launch_fwd<256>(F, HW, partials, plan, stream);
+    case 512: return launch_fwd<512>(F, HW, partials, plan, stream);
+  }
+  set_error("gram_tc_fwd: unsupported C=%d", C);
+  return AST_ERR_UNSUPPORTED;
+}
+
+template <int C>
+static int launch_bwd(const float* D, const float* F, int64_t HW, float scale, const float* gscale, float* dF,
+                      int accumulate, int num_sms, cudaStream_t stream) {
+  using Cfg = BwdCfg<C>;
+  CUtensorMap tmF, tmD;
+  int rc = make_tmap(&tmF, F, C, HW, 32);
+  if (rc != AST_OK) return rc;
+  rc = make_tmap(&tmD, D, C, C, Cfg::kDBoxRows);
+  if (rc != AST_OK) return rc;
+  BwdParams P;
+  P.HW = HW;
+  P.n_tiles = (int)((HW + 127) / 128);
+  P.scale = scale;
+  P.gscale = gscale;
+  P.accumulate = accumulate;
+  P.dF = dF;
+  cudaError_t e = cudaFuncSetAttribute(gram_bwd_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (e != cudaSuccess) {
+    set_error("gram_tc_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return AST_ERR_CUDA;
+  }
+  const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
+  gram_bwd_tc_kernel<C><<<grid, 320, Cfg::kSmemBytes, stream>>>(tmF, tmD, P);
+  return check_launch("gram_bwd_tc");
+}
+
+int gram_tc_bwd(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale, float* dF,
+                int accumulate, int num_sms, cudaStream_t stream) {
+  switch (C) {
+    case 64: return launch_bwd<64>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
+    case 128: return launch_bwd<128>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
+    case 256: return launch_bwd<256>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
+    case 512: return launch_bwd<512>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
+  }
+  set_error("gram_tc_bwd: unsupported C=%d", C);
+  return AST_ERR_UNSUPPORTED;
+}
+
+}  // namespace ast

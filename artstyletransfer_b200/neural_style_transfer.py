@@ -1,0 +1,386 @@
+"""Drop-in for the reference's neural_style_transfer.py: same classes, functions, signatures, generator
+protocol and error behaviour, with the pyramid Gatys-loss hot path running in libast_sm100.so.
+
+Kept from the reference (file:line into its neural_style_transfer.py):
+  ContentStylePair :32-36 · RepresentationBuilder :39-63 · LossBuilder :66-112 · NeuralStyleTransfer.process
+  :115-208 (async generator, torch Adam/LBFGS driver, lr*0.999 per closure, `step` counts closures,
+  optimizer.step runs on the asyncio default executor) · resize :211-226 · neural_style_transfer :229-372 ·
+  prepare_img/unprepare_img :375-393 · gaussian_mask :396-418 · make_style_noise :422-439 · the constants and
+  the four demo flags :22-29.
+
+Dropped because they are exactly zero or pure overhead: the `0 * clip(randn)` tensor built on the
+CPU every closure (:91-93), set_detect_anomaly(True) (:150), the per-level `.item()` prints (:159-196; enable
+with VERBOSE = True), the deepcopy before the per-step device->host copy (:207).
+"""
+from __future__ import annotations
+
+import asyncio
+import os
+import traceback
+
+import numpy as np
+import torch
+from torch import Tensor
+from torch.autograd import Variable
+from torch.optim import Adam, LBFGS
+
+from . import math_utils, ops
+from . import parallel as _parallel
+
+# ImageNet statistics (:22-23)
+IMAGENET_MEAN_255 = [123.675, 116.28, 103.53]
+IMAGENET_STD_NEUTRAL = [1, 1, 1]
+
+# Flags for debug/demonstration (:26-29)
+USE_NORMAL_NOISE_JUST_FOR_DEMONSTRATION = False
+WITHOUT_GAUSSIAN_MASK_JUST_FOR_DEMONSTRATION = False
+SHOW_TEST_IMGS = False          # accepted for compatibility; the debug JPEG dumps are not produced
+IGNORE_GRADIENT_MAP_JUST_FOR_DEMONSTRATION = False
+
+VERBOSE = False                 # True restores the reference's per-closure prints (adds host syncs)
+PRECISION = None                # None -> ops.DEFAULT_PRECISION ('tf32'); 'fp32' for the exact path
+
+
+class ContentStylePair:
+    """ Pairs content image - style image """
+    def __init__(self, content, style):
+        self.content = content      # (content_img_name, content_img)
+        self.style = style          # (style_img_name, style_img)
+
+
+class RepresentationBuilder:
+    """Content / style representations of an image from the network's feature maps (:39-63)."""
+    def __init__(self, image, neural_net):
+        self.__image = image
+        self.__neural_net = neural_net
+        self.__features = neural_net(image)
+
+    def build_content(self, feature_map_indices: int | list[int]):
+        list_taken = isinstance(feature_map_indices, list)
+        indices = feature_map_indices if list_taken else [feature_map_indices]
+        rep = [x.squeeze(axis=0) for index, x in enumerate(self.__features) if index in indices]
+        return rep if list_taken else rep[0]
+
+    def build_style(self, feature_map_indices: int | list[int]):
+        list_taken = isinstance(feature_map_indices, list)
+        indices = feature_map_indices if list_taken else [feature_map_indices]
+        rep = [math_utils.gram_matrix(x, precision=PRECISION) for index, x in enumerate(self.__features)
+               if index in indices]
+        return rep if list_taken else rep[0]
+
+
+class LossBuilder:
+    """One pyramid level's loss (:66-112).  Targets are built once at construction (:78-82); build() runs the
+    VGG forward on torch/cuDNN and then ONE fused autograd node: 5 x (split-K tcgen05 Gram + fused MSE),
+    content MSE, TV, weighted sum — and, backward, (G-A)F per layer, 2(X-T)/n and the TV gradient."""
+    def __init__(self, content_feature_maps_index, style_feature_maps_indices, target_content_image,
+                 target_style_image, neural_net, content_weight, style_weight, tv_weight):
+        self.__content_feature_maps_index = content_feature_maps_index
+        self.__style_feature_maps_indices = style_feature_maps_indices
+        self.__neural_net = neural_net
+        self.__content_weight = content_weight
+        self.__style_weight = style_weight
+        self.__tv_weight = tv_weight
+        with torch.no_grad():
+            content_rep_builder = RepresentationBuilder(image=target_content_image, neural_net=neural_net)
+            self.__target_content_representation = \
+                content_rep_builder.build_content(content_feature_maps_index).detach().clone().contiguous()
+            del content_rep_builder
+            style_rep_builder = RepresentationBuilder(image=target_style_image, neural_net=neural_net)
+            self.__target_style_representation = style_rep_builder.build_style(style_feature_maps_indices)
+            del style_rep_builder
+        self.__target_grams = [g[0].detach().contiguous() for g in self.__target_style_representation]
+        self.__wss = ops.LevelWorkspaces()
+        self.shard = None           # set by parallel.shard_loss_builders for row-band sharded levels
+
+    @property
+    def target_content_representation(self):
+        return self.__target_content_representation
+
+    @property
+    def target_style_representation(self):
+        return self.__target_style_representation
+
+    def build(self, optimizing_img):
+        if self.shard is not None:
+            return self.shard.build(optimizing_img)
+        feats = self.__neural_net(optimizing_img)
+        cfg = (self.__target_content_representation, self.__target_grams,
+               (self.__content_weight, self.__style_weight, self.__tv_weight), self.__wss, ops._prec(PRECISION))
+        total_loss, content_loss, style_loss, tv_loss = ops.LevelLossFn.apply(
+            cfg, optimizing_img, feats[self.__content_feature_maps_index],
+            *[feats[k] for k in self.__style_feature_maps_indices])
+        return total_loss, content_loss, style_loss, tv_loss
+
+
+class NeuralStyleTransfer:
+    """ The main class for calculating of artistic style transfer (:115-208) """
+    def __init__(self, device, model_name, style_imgs, optimizer_name):
+        self.__device = device
+        self.__model_name = model_name
+        self.__style_imgs = style_imgs
+        self.__optimizer_name = optimizer_name
+
+    async def process(self, content_imgs, init_img, lr_start, iters_num, content_weight, style_weight, tv_weight,
+                      init_img_name):
+        device = torch.device(self.__device)
+        if device.type != 'cuda':
+            raise RuntimeError('artstyletransfer_b200 runs the Gatys-loss path on sm_100a CUDA only; '
+                               f'got device {device} (no CPU fallback)')
+        neural_net, content_feature_maps_index, style_feature_maps_indices = \
+            math_utils.prepare_model(self.__model_name, device)
+        if VERBOSE:
+            print(f'Using {self.__model_name} in the optimization procedure.')
+
+        init_img = prepare_img(init_img, device)
+        # we are tuning optimizing_img's pixels! (that's why requires_grad=True)
+        optimizing_img = Variable(init_img, requires_grad=True)
+
+        if self.__optimizer_name == 'adam':
+            optimizer = Adam((optimizing_img,), lr=lr_start)
+        elif self.__optimizer_name == 'lbfgs':
+            optimizer = LBFGS((optimizing_img,), max_iter=1, line_search_fn='strong_wolfe', lr=lr_start)
+        else:
+            raise RuntimeError("Unknown optimizer")
+
+        loss_builders = []
+        for content_img, style_img in zip(content_imgs, self.__style_imgs):
+            content_img = prepare_img(content_img, device)
+            style_img = prepare_img(style_img, device)
+            loss_builders.append(LossBuilder(content_feature_maps_index, style_feature_maps_indices, content_img,
+                                             style_img, neural_net, content_weight, style_weight, tv_weight))
+        _parallel.maybe_shard(loss_builders, optimizing_img, neural_net, content_feature_maps_index,
+                              style_feature_maps_indices, (content_weight, style_weight, tv_weight))
+
+        step = 0
+
+        def optimizer_step_callback():
+            try:
+                # learning rate schedule (:155-159)
+                lr = 0
+                for g in optimizer.param_groups:
+                    g['lr'] *= 0.999
+                    lr = g['lr']
+                nonlocal step
+                if torch.is_grad_enabled():
+                    optimizer.zero_grad()
+                if VERBOSE:
+                    print(f"new lr = {lr}")
+                    print(f'{self.__optimizer_name} | processing image: {init_img_name} | iteration: {step:03} :')
+                optimizing_img_levels = None
+                total_loss = None
+                for i in range(len(loss_builders)):
+                    # lower resolutions of optimizing_img: chained bicubic 2x down (:168-176)
+                    if i == 0:
+                        optimizing_img_levels = [optimizing_img]
+                    else:
+                        optimizing_img_levels.append(ops.bicubic_half(optimizing_img_levels[i - 1]))
+                    total_loss_l, content_loss, style_loss, tv_loss = loss_builders[i].build(optimizing_img_levels[i])
+                    if total_loss is None:
+                        total_loss = total_loss_l
+                    else:
+                        previous_loss_importance = 1.0
+                        total_loss = previous_loss_importance * total_loss + total_loss_l
+                    if VERBOSE:
+                        with torch.no_grad():
+                            print(f' - level {i} | level loss={total_loss_l.item():.3e}, '
+                                  f'content_loss={content_weight * content_loss.item():.3e}, '
+                                  f'style loss={style_weight * style_loss:.3e}, '
+                                  f'tv loss={tv_weight * tv_loss.item():.3e}')
+                if total_loss.requires_grad:
+                    total_loss.backward()
+                    _parallel.sync_image_grad(optimizing_img)
+                if VERBOSE:
+                    with torch.no_grad():
+                        print(f'{self.__optimizer_name} | total loss={total_loss.item():.3e}')
+                step += 1
+                return total_loss
+            except:
+                traceback.print_exc()
+                raise
+
+        # the main optimization loop (:205-208)
+        while step < iters_num:
+            await asyncio.get_running_loop().run_in_executor(None, optimizer.step, optimizer_step_callback)
+            yield unprepare_img(optimizing_img), step
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError('artstyletransfer_b200 needs a CUDA device (B200, sm_100a); no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def level_size(img, level):
+    """(new_height, new_width) of pyramid `level` (:213-224; int() truncation of the long side)."""
+    base_diameter = 256
+    current_height, current_width = img.shape[:2]
+    if current_height >= current_width:
+        base_width = base_diameter
+        base_height = int(base_width * (current_height / current_width))
+    else:
+        base_height = base_diameter
+        base_width = int(base_height * (current_width / current_height))
+    return base_height * pow(2, level), base_width * pow(2, level)
+
+
+def _resize_hwc_device(img_dev, new_h, new_w):
+    return ops.bicubic_resize(img_dev, new_h, new_w, layout='hwc', coord='cv2')
+
+
+async def resize(img, level):
+    """ A function for proper resizing of an image according to the level of pyramid (:211-226).
+    Same result as cv2.resize(..., INTER_CUBIC) on float32 images, computed by the K6 kernel. """
+    new_height, new_width = level_size(img, level)
+    dev = _device()
+    src = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32)).to(dev)
+    if src.dim() == 2:
+        src = src.unsqueeze(-1)
+    out = _resize_hwc_device(src, new_height, new_width).cpu().numpy()
+    return out if img.ndim == 3 else out[:, :, 0]
+
+
+async def neural_style_transfer(content_n_style: ContentStylePair,
+                                content_weight, style_weight, tv_weight,
+                                optimizer, model, init_method,
+                                iters_num, levels_num, noise_factor, noise_levels, noise_levels_central_amplitude,
+                                noise_levels_peripheral_amplitude, noise_levels_dispersion):
+    """ The main function (:229-372) """
+    device = _device()
+    model_name = model
+    optimizer_name = optimizer
+
+    # pyramids of the content and style images, high -> low resolution (:250-263)
+    level = 0
+    content_img_levels = [await resize(content_n_style.content[1], level=level)]
+    style_img_levels = [await resize(content_n_style.style[1], level=level)]
+    for level in range(1, levels_num):
+        content_img_levels.insert(0, await resize(content_n_style.content[1], level=level))
+        style_img_levels.insert(0, await resize(content_n_style.style[1], level=level))
+
+    init_img_next, init_img_name = build_init_image(
+        content_n_style, content_img_levels, style_img_levels, init_method, noise_factor, noise_levels,
+        noise_levels_central_amplitude, noise_levels_peripheral_amplitude, noise_levels_dispersion, device)
+
+    nst = NeuralStyleTransfer(device, model_name, style_img_levels, optimizer_name)
+    lr_start = 10.0
+    async for img, cur_iter in nst.process(content_img_levels, init_img_next, lr_start, iters_num, content_weight,
+                                           style_weight, tv_weight, init_img_name):
+        percent = cur_iter / iters_num * 100.0
+        cur_iter += 1
+        yield percent, img
+
+
+def gaussian_kernel_1d(n, sigma):
+    """cv2.getGaussianKernel(n, sigma) (CV_64F) as OpenCV >= 4 computes it: exp(-x^2/(2 sigma^2)) normalised,
+    with the two centre taps of an EVEN-length kernel set to the x = 0 value before normalisation."""
+    if sigma <= 0:
+        sigma = ((n - 1) * 0.5 - 1) * 0.3 + 0.8
+    i = np.arange(n, dtype=np.float64) - (n - 1) * 0.5
+    g = np.exp(-(i * i) / (2.0 * sigma * sigma))
+    if n % 2 == 0:
+        g[n // 2 - 1] = g[n // 2] = 1.0
+    return g / g.sum()
+
+
+def gaussian_mask(shape, central_amplitude, peripheral_amplitude, dispersion_scale=0.5):
+    """ Gaussian envelope for the noise map (:396-418): (rows, cols, 3) float64.  Host helper kept for API parity;
+    the init kernel evaluates the same separable envelope on the fly from the two 1-D vectors. """
+    rows, cols = shape[:2]
+    gx = gaussian_kernel_1d(cols, cols * dispersion_scale)
+    gy = gaussian_kernel_1d(rows, rows * dispersion_scale)
+    resultant_kernel = np.outer(gy, gx)
+    gauss_norm = resultant_kernel / resultant_kernel[rows // 2, cols // 2]
+    mask = peripheral_amplitude + gauss_norm * (central_amplitude - peripheral_amplitude)
+    return np.repeat(np.expand_dims(mask, 2), 3, axis=2)
+
+
+def make_style_noise(style_img_np, targ_shape):
+    """ Noise map made by randomly permuting the pixels of the (resized) style image (:422-439).
+    The resize runs on the device; the permutation uses numpy's legacy global RNG exactly like the reference. """
+    nw = targ_shape[1]
+    nh = targ_shape[0]
+    dev = _device()
+    src = torch.from_numpy(np.ascontiguousarray(style_img_np, dtype=np.float32)).to(dev)
+    style_img_np_resized = _resize_hwc_device(src, nh, nw).cpu().numpy()
+    style_vect = style_img_np_resized.reshape(nh * nw, -1)
+    style_noise_vect = np.random.permutation(style_vect)
+    return style_noise_vect.reshape(targ_shape)
+
+
+def build_init_image(content_n_style, content_img_levels, style_img_levels, init_method, noise_factor,
+                     noise_levels, noise_levels_central_amplitude, noise_levels_peripheral_amplitude,
+                     noise_levels_dispersion, device):
+    """Structured-noise initial image (:265-362) -> (HxWx3 float32 numpy, name).  Host: numpy RNG draws, low-res
+    grids, 1-D Gaussian vectors.  Device: one fused K7 pass (upsample x envelope accumulation, Sobel map, blend)."""
+    if init_method not in ('random', 'content+noise'):
+        # init image has same dimension as content image - this is a hard constraint (:358-362)
+        return style_img_levels[0], content_n_style.style[0]
+
+    noise_shape = content_img_levels[0].shape
+    nw = noise_shape[1]
+    nh = noise_shape[0]
+    levels = []
+    for noise_granularity, central_amplitude, peripheral_amplitude, dispersion_scale in zip(
+            noise_levels, noise_levels_central_amplitude, noise_levels_peripheral_amplitude, noise_levels_dispersion):
+        entry = {'central': central_amplitude, 'peripheral': peripheral_amplitude}
+        with_mask = noise_granularity == 0 or not WITHOUT_GAUSSIAN_MASK_JUST_FOR_DEMONSTRATION
+        if with_mask:
+            gx = gaussian_kernel_1d(nw, nw * dispersion_scale)
+            gy = gaussian_kernel_1d(nh, nh * dispersion_scale)
+            entry.update(gy=torch.from_numpy(gy).to(device), gx=torch.from_numpy(gx).to(device),
+                         center=float(gy[nh // 2] * gx[nw // 2]))
+        if noise_granularity == 0:
+            entry['kind'] = 0           # constant level: envelope only (:272-275)
+        else:
+            if noise_granularity > 0:   # number of noise spots along the shortest axis (:277-287)
+                if nh <= nw:
+                    noise_shape_div_h = noise_granularity
+                    noise_shape_div_w = nw * noise_granularity // nh
+                else:
+                    noise_shape_div_w = noise_granularity
+                    noise_shape_div_h = nh * noise_granularity // nw
+            else:                       # spot size in pixels (:288-291)
+                noise_shape_div_w = nw // (-noise_granularity)
+                noise_shape_div_h = nh // (-noise_granularity)
+            noise_shape_div = (noise_shape_div_h, noise_shape_div_w, noise_shape[2])
+            if USE_NORMAL_NOISE_JUST_FOR_DEMONSTRATION:
+                lowres = np.clip(np.random.normal(loc=0, scale=255, size=noise_shape_div).astype(np.float32) / 255,
+                                 0.0, 1.0)
+            else:
+                lowres = make_style_noise(style_img_levels[0], noise_shape_div)
+            entry['lowres'] = torch.from_numpy(np.ascontiguousarray(lowres, dtype=np.float32)).to(device)
+            entry['kind'] = 1 if with_mask else 2
+        levels.append(entry)
+
+    g101 = gaussian_kernel_1d(101, 0.2)     # GaussianBlur((101,101), sigmaX=0.2) (:340): taps beyond +-1 < 2e-22
+    content_dev = None
+    if init_method == 'content+noise':
+        content_dev = torch.from_numpy(np.ascontiguousarray(content_img_levels[0], dtype=np.float32)).to(device)
+    out = ops.noise_init(content_dev, nh, nw, levels, noise_factor, init_method,
+                         not IGNORE_GRADIENT_MAP_JUST_FOR_DEMONSTRATION, g101[50], g101[49], device)
+    name = 'random' if init_method == 'random' else content_n_style.content[0]
+    return out.cpu().numpy(), name
+
+
+def prepare_img(img, device):
+    """ HWC float [0,1] -> (1,3,H,W): x*255 - ImageNet mean, std 1 (:375-383) """
+    if isinstance(img, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(img.transpose((2, 0, 1))))
+        if t.dtype == torch.uint8:
+            t = t.to(torch.float32).div(255)   # torchvision ToTensor semantics for uint8
+        t = t.to(torch.float32)
+    else:
+        t = img.to(torch.float32)
+    t = t.to(device)
+    mean = torch.tensor(IMAGENET_MEAN_255, dtype=torch.float32, device=t.device).view(3, 1, 1)
+    std = torch.tensor(IMAGENET_STD_NEUTRAL, dtype=torch.float32, device=t.device).view(3, 1, 1)
+    return t.mul(255).sub_(mean).div_(std).unsqueeze(0)
+
+
+def unprepare_img(img: Tensor):
+    """ Reverse of prepare_img (:388-393): (1,3,H,W) device tensor -> HxWx3 float32 numpy on the host """
+    dump_img = img.detach().permute([0, 2, 3, 1]).squeeze(0).to("cpu").numpy()
+    dump_img += np.array(IMAGENET_MEAN_255).reshape((1, 1, 3))
+    dump_img = dump_img.astype(np.float32) / 255
+    return dump_img

@@ -1,0 +1,157 @@
+/*
+ * ast_sm100.h — C ABI of libast_sm100.so: the pyramid Gatys-loss hot path of
+ * irenemizus/ArtStyleTransfer as hand-written sm_100a (B200) CUDA.
+ *
+ * The reference has no FFI of its own (it is pure Python on torch / OpenCV); the boundary it
+ * offers is its Python call surface.  Each entry point below replaces the library call the
+ * reference makes at the cited site (file:line into the reference repository).  The Python
+ * binding a maintainer would add is the ctypes stub in INTEGRATION.md (shipped as
+ * artstyletransfer_b200/_lib.py).
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, sizes, a cudaStream_t passed as void*; no torch types;
+ *   - every call only enqueues work on `stream`; it never synchronises and never allocates;
+ *   - return 0 on success, a negative AST_ERR_* otherwise; ast_last_error() (thread-local)
+ *     holds the message;
+ *   - no hidden mutable state: scratch memory is caller-provided (`ws`).  A workspace must be
+ *     zero-filled once when allocated; kernels leave it reusable.  Two host threads may call
+ *     concurrently as long as they pass different workspaces (the reference runs closures of
+ *     up to 2 jobs from different threads — task_executor.py:9, neural_style_transfer.py:206);
+ *   - all tensors are contiguous fp32.  Feature maps are (C, HW) row-major, i.e. torch NCHW
+ *     with batch 1; images are (C, H, W) unless a layout argument says otherwise.
+ */
+#ifndef AST_SM100_H_
+#define AST_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AST_ABI_VERSION 1
+
+#define AST_OK               0
+#define AST_ERR_INVALID     -1   /* bad argument (null pointer, non-positive size, misalignment) */
+#define AST_ERR_CUDA        -2   /* a CUDA runtime / driver call failed                          */
+#define AST_ERR_UNSUPPORTED -3   /* shape or mode not implemented by this build                  */
+#define AST_ERR_WORKSPACE   -4   /* workspace too small                                          */
+
+/* Operand precision of the Gram contractions (accumulation is always fp32). */
+#define AST_PREC_TF32 0   /* tcgen05 kind::tf32, operands rounded to nearest TF32 in shared memory */
+#define AST_PREC_FP32 1   /* exact fp32 FFMA path (what torch.bmm does with allow_tf32 = False)    */
+
+#define AST_LAYOUT_CHW 0
+#define AST_LAYOUT_HWC 1
+
+/* Source-coordinate arithmetic of the bicubic resampler (both: Keys A=-0.75, per-tap clamp). */
+#define AST_COORD_TORCH 0 /* F.interpolate(mode='bicubic'): float scale, float source index  */
+#define AST_COORD_CV2   1 /* cv2.resize(INTER_CUBIC): double scale, index cast to float      */
+
+int         ast_version(void);
+const char* ast_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x (B200), AST_ERR_UNSUPPORTED otherwise. */
+int         ast_device_check(void);
+
+/* ---- Gram matrix + fused MSE --------------------------------------------------------------
+ * Replaces math_utils.gram_matrix (math_utils.py:26-34: view, transpose, bmm, /= ch*h*w) and
+ * the per-layer torch.nn.MSELoss against the target Gram (neural_style_transfer.py:100-104).
+ *
+ *   out[C,C] = scale * F F^T - (A ? A : 0);    *loss = mean(out^2) over C*C   (if loss != NULL)
+ *
+ * Single GPU: scale = 1/(C*HW), A = target Gram -> out is D = G - A, loss the layer's MSE.
+ * Plain Gram: A = NULL, loss = NULL.  Row-band sharding: scale = 1, A = NULL gives the raw
+ * partial sum to all-reduce, then ast_gram_finalize applies scale / A / MSE on every rank.
+ * ws must hold ast_gram_workspace_bytes(C, HW) bytes.
+ */
+size_t ast_gram_workspace_bytes(int C, int64_t HW);
+int ast_gram_mse_fwd(const float* F, int C, int64_t HW, float scale, const float* A,
+                     float* out, float* loss, void* ws, size_t ws_bytes, int precision,
+                     void* stream);
+int ast_gram_finalize(const float* G_raw, int C, float scale, const float* A, float* out,
+                      float* loss, void* ws, size_t ws_bytes, void* stream);
+
+/* Backward of the style term (autograd of bmm + MSELoss in the reference, 2 bmm per layer):
+ *   dF[C,HW] (+)= scale * D D-symmetric [C,C] * F[C,HW]
+ * with scale = 4 / (C^2 * C*HW) on the host and the upstream gradient read on the device:
+ * every *_bwd entry point multiplies its host scale by *gscale when gscale != NULL (a device
+ * float, e.g. autograd's grad_output), so no host synchronisation is needed. */
+int ast_gram_bwd(const float* D, const float* F, int C, int64_t HW, float scale,
+                 const float* gscale, float* dF, int accumulate, int precision, void* stream);
+
+/* ---- Content MSE (neural_style_transfer.py:95) ---------------------------------------------
+ *   *loss = scale * sum((X - T)^2)      (scale = 1/n for MSELoss(reduction='mean'))
+ *   dX (+)= scale * (X - T)             (scale = 2 * content_weight / n * upstream)       */
+size_t ast_reduce_workspace_bytes(void);
+int ast_mse_fwd(const float* X, const float* T, int64_t n, float scale, float* loss, void* ws,
+                size_t ws_bytes, void* stream);
+int ast_mse_bwd(const float* X, const float* T, int64_t n, float scale, const float* gscale,
+                float* dX, int accumulate, void* stream);
+
+/* ---- Total variation (math_utils.py:37-41) -------------------------------------------------
+ *   sums[0] = sum |y[..., :-1] - y[..., 1:]|,  sums[1] = sum |y[:, :-1, :] - y[:, 1:, :]|
+ *   *tv = (sums[0]/nx)^2 + (sums[1]/ny)^2 with nx = C*H*(W-1), ny = C*(H-1)*W  (tv may be NULL)
+ *   dY (+)= kx*sums[0]*d|dx|/dy + ky*sums[1]*d|dy|/dy ;  kx = 2*w*upstream/nx^2, ky likewise */
+int ast_tv_fwd(const float* Y, int C, int H, int W, float* sums2, float* tv, void* ws,
+               size_t ws_bytes, void* stream);
+int ast_tv_bwd(const float* Y, int C, int H, int W, const float* sums2, float kx, float ky,
+               const float* gscale, float* dY, int accumulate, void* stream);
+
+/* ---- Level loss assembly (neural_style_transfer.py:100-110) ---------------------------------
+ *   out4 = { total, content, style, tv } with style = mean(style_mse[0..n_style)) and
+ *   total = content_weight*content + style_weight*style + tv_weight*tv.   One tiny launch
+ *   instead of ~10 scalar torch kernels per level. */
+int ast_level_combine(const float* style_mse, int n_style, const float* content, const float* tv,
+                      float content_weight, float style_weight, float tv_weight, float* out4,
+                      void* stream);
+
+/* ---- Bicubic pyramid of the optimizing image (neural_style_transfer.py:168-176) -------------
+ * y = F.interpolate(x, size=(H/2, W/2), mode='bicubic') for even H, W: fixed taps
+ * [-3/32, 19/32, 19/32, -3/32] at rows/cols 2d-1..2d+2 with clamped borders; *_adj is its exact
+ * transpose in gather form (deterministic, replaces upsample_bicubic2d_backward's atomics). */
+int ast_bicubic_down2x(const float* x, int C, int H, int W, float* y, void* stream);
+int ast_bicubic_down2x_adj(const float* gy, int C, int H, int W, float* gx, int accumulate,
+                           void* stream);
+/* General ratio (odd pyramid sizes; cv2.resize(..., INTER_CUBIC) at
+ * neural_style_transfer.py:226, :304, :427).  The adjoint is CHW only. */
+int ast_bicubic_resize(const float* x, int C, int Hin, int Win, float* y, int Hout, int Wout,
+                       int layout, int coord_mode, void* stream);
+int ast_bicubic_resize_adj(const float* gy, int C, int Hin, int Win, int Hout, int Wout,
+                           float* gx, int accumulate, int coord_mode, void* stream);
+
+/* ---- Structured-noise init (neural_style_transfer.py:265-362, :396-418) ---------------------
+ * One fused pass over the top-level image:
+ *   acc   = sum over levels of   kind 0: envelope | kind 1: up(lowres)*envelope | kind 2: up(lowres)
+ *           (float32 accumulation per level, as the reference's in-place += on a float32 array)
+ *   envelope(y,x) = peripheral + gy[y]*gx[x]/center*(central - peripheral)           (fp64)
+ *   mode AST_INIT_RANDOM        : out = acc * 0.5
+ *   mode AST_INIT_CONTENT_NOISE : r = 5*noise_factor/(5 + blur(clip(|Sobel5|, 0, 100)));
+ *                                 out = (1-r)*content + r*acc   (fp64, cast to fp32)
+ *                                 (use_gradient_map = 0 -> r = noise_factor everywhere)
+ * Random numbers stay on the host (numpy legacy RNG, for parity); lowres grids are device
+ * pointers to (lh, lw, 3) float32 HWC.  gy/gx: device fp64 vectors of length H / W
+ * (cv2.getGaussianKernel).  content/out: (H, W, 3) float32 HWC. */
+#define AST_INIT_RANDOM        0
+#define AST_INIT_CONTENT_NOISE 1
+#define AST_NOISE_MAX_LEVELS   16
+typedef struct ast_noise_level {
+  const float*  lowres;      /* device, (lh, lw, 3) HWC; NULL for kind 0                      */
+  int32_t       lh, lw;
+  int32_t       kind;        /* 0 envelope only, 1 noise*envelope, 2 noise only               */
+  int32_t       pad_;
+  const double* gy;          /* device, length H                                              */
+  const double* gx;          /* device, length W                                              */
+  double        center;      /* gy[H/2] * gx[W/2] (the reference divides by this element)     */
+  double        central, peripheral;
+} ast_noise_level;
+/* blur_w0 / blur_w1: centre and +-1 taps of cv2.getGaussianKernel(101, 0.2) (the remaining taps
+ * are < 2e-22 and dropped). */
+int ast_noise_init(const float* content_hwc, int H, int W, const ast_noise_level* levels,
+                   int n_levels, double noise_factor, int mode, int use_gradient_map,
+                   double blur_w0, double blur_w1, float* out_hwc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AST_SM100_H_ */

@@ -27,3 +27,21 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
     return load
+
+
+@pytest.fixture()
+def seeded_vgg(monkeypatch):
+    """Patch the product's neural_nets.models.vgg19 (hard-coded pretrained=True, like the reference's
+    neural_nets.py:19) with a seeded random-init VGG19 — the same shim the goldens were generated with."""
+    import torch
+    import torchvision
+    from artstyletransfer_b200 import neural_nets
+
+    real = torchvision.models.vgg19
+
+    def seeded(pretrained=False, progress=False, **kw):
+        torch.manual_seed(1234)
+        return real(weights=None)
+
+    monkeypatch.setattr(neural_nets.models, 'vgg19', seeded)
+    return seeded

@@ -1,0 +1,116 @@
+"""CPU: the C-ABI library loads, exports every symbol include/ast_sm100.h declares, and validates its
+arguments (no kernel is launched without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    import __graft_entry__ as entry
+    entry.build()
+    from artstyletransfer_b200 import _lib
+    return _lib.load()
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, 'include', 'ast_sm100.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    return sorted(set(re.findall(r'\b(ast_[a-z0-9_]+)\s*\(', hdr)))
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    from artstyletransfer_b200 import _lib
+    syms = declared_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), f'{s} declared in ast_sm100.h but not exported'
+        assert s in _lib.SIGNATURES, f'{s} has no ctypes signature'
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_version_and_sizes(lib):
+    assert lib.ast_version() == 1
+    assert lib.ast_reduce_workspace_bytes() >= 16384
+    # workspace covers 148 split-K partials of the largest tile plus the reduce header
+    assert lib.ast_gram_workspace_bytes(512, 98304) == 32768 + 148 * 256 * 256 * 4
+    assert lib.ast_gram_workspace_bytes(64, 6291456) >= 32768 + 148 * 2 * 64 * 64 * 4
+    assert lib.ast_gram_workspace_bytes(0, 10) == 0
+
+
+def test_argument_validation_without_gpu(lib):
+    from artstyletransfer_b200 import _lib
+    rc = lib.ast_mse_fwd(None, None, 10, 1.0, None, None, 0, None)
+    assert rc == -1 and b'null pointer' in lib.ast_last_error()
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.addressof(buf)
+    rc = lib.ast_bicubic_down2x(p, 3, 7, 8, p, None)
+    assert rc == -3 and b'even' in lib.ast_last_error()
+    rc = lib.ast_gram_mse_fwd(p, 48, 64, 1.0, None, p, None, p, 1 << 30, 0, None)
+    assert rc == -3 and b'multiple of 64' in lib.ast_last_error()
+    rc = lib.ast_gram_mse_fwd(p, 64, 64, 1.0, None, p, None, p, 16, 0, None)
+    assert rc == -4
+    with pytest.raises(RuntimeError, match='ast_mse_bwd failed'):
+        _lib.call('ast_mse_bwd', None, None, 1, 1.0, None, None, 0, None)
+
+
+def test_cpu_tensors_fail_loudly(lib):
+    import torch
+    from artstyletransfer_b200 import math_utils, ops
+    with pytest.raises(RuntimeError, match='CUDA'):
+        math_utils.gram_matrix(torch.zeros(1, 64, 4, 4))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.bicubic_half(torch.zeros(1, 3, 8, 8))
+
+
+def test_shim_modules_expose_reference_names(lib):
+    import importlib
+    import sys
+    shim = os.path.join(ROOT, 'artstyletransfer_b200', 'shim')
+    sys.path.insert(0, shim)
+    try:
+        for mod in ('config', 'neural_nets', 'math_utils', 'neural_style_transfer'):
+            sys.modules.pop(mod, None)
+        mu = importlib.import_module('math_utils')
+        nn_ = importlib.import_module('neural_nets')
+        nst = importlib.import_module('neural_style_transfer')
+        cfg = importlib.import_module('config')
+    finally:
+        sys.path.remove(shim)
+        for mod in ('config', 'neural_nets', 'math_utils', 'neural_style_transfer'):
+            sys.modules.pop(mod, None)
+    for name in ('prepare_model', 'gram_matrix', 'total_variation', 'regularization'):
+        assert callable(getattr(mu, name))
+    for name in ('Vgg19', 'StyleLoss', 'ContentLoss'):
+        assert isinstance(getattr(nn_, name), type)
+    for name in ('ContentStylePair', 'RepresentationBuilder', 'LossBuilder', 'NeuralStyleTransfer', 'resize',
+                 'neural_style_transfer', 'prepare_img', 'unprepare_img', 'gaussian_mask', 'make_style_noise',
+                 'IMAGENET_MEAN_255', 'USE_NORMAL_NOISE_JUST_FOR_DEMONSTRATION',
+                 'WITHOUT_GAUSSIAN_MASK_JUST_FOR_DEMONSTRATION', 'SHOW_TEST_IMGS',
+                 'IGNORE_GRADIENT_MAP_JUST_FOR_DEMONSTRATION'):
+        assert hasattr(nst, name), name
+    c = cfg.Config()
+    assert (c.content_weight, c.style_weight, c.tv_weight, c.optimizer, c.levels_num, c.iters_num) == \
+           (1e3, 4e5, 1e2, 'lbfgs', 2, 500)
+    assert cfg.simultaneous_tasks_count == 2
+    with pytest.raises(ValueError):
+        mu.prepare_model('alexnet', 'cpu')
+
+
+def test_process_rejects_unknown_optimizer_and_cpu(lib):
+    import asyncio
+    import numpy as np
+    from artstyletransfer_b200 import neural_style_transfer as nst
+
+    async def run(device, opt):
+        drv = nst.NeuralStyleTransfer(device, 'vgg19', [np.zeros((32, 32, 3), np.float32)], opt)
+        async for _ in drv.process([np.zeros((32, 32, 3), np.float32)], np.zeros((32, 32, 3), np.float32), 10.0, 1,
+                                   1e3, 4e5, 1e2, 'x'):
+            pass
+
+    with pytest.raises(RuntimeError, match='CUDA only'):
+        asyncio.run(run('cpu', 'adam'))

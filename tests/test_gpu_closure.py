@@ -1,0 +1,157 @@
+"""GPU parity of the whole closure and of the driver loop, through the product's public (reference-shaped)
+API, vs (i) the oracle's torch restatement run on the SAME device (same cuDNN features — the apples-to-apples
+"reference torch path on this box") and (ii) the goldens produced by the unmodified reference on CPU.
+
+Tolerances (BASELINE.json): total loss relative error <= 1e-4; final image PSNR >= 40 dB."""
+import asyncio
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gatys_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+WEIGHTS = (1e3, 4e5, 1e2)
+
+
+def dev():
+    return torch.device('cuda', 0)
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(autouse=True)
+def exact_convs():
+    """Make cuDNN convolutions fp32-exact and repeatable so that the two closures see identical features."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic = old
+
+
+def product_closure(nst, net, cidx, sidx, c_levels, s_levels, init):
+    builders = [nst.LossBuilder(cidx, sidx, nst.prepare_img(c, dev()), nst.prepare_img(s, dev()), net, *WEIGHTS)
+                for c, s in zip(c_levels, s_levels)]
+    from artstyletransfer_b200 import ops
+    img = nst.prepare_img(init, dev()).requires_grad_(True)
+    levels = [img]
+    total = None
+    per = []
+    for i, b in enumerate(builders):
+        if i > 0:
+            levels.append(ops.bicubic_half(levels[i - 1]))
+        t, c, s, v = b.build(levels[i])
+        per.append([t.item(), c.item(), s.item(), v.item()])
+        total = t if total is None else 1.0 * total + t
+    total.backward()
+    return total.item(), np.array(per), img.grad.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32'])
+@pytest.mark.parametrize('nlev', [1, 2])
+def test_closure_vs_reference_golden_and_oracle(golden, seeded_vgg, nlev, precision):
+    from artstyletransfer_b200 import math_utils, neural_style_transfer as nst
+    gd = golden('closure.npz')
+    nst.PRECISION = precision
+    try:
+        net, cidx, sidx = math_utils.prepare_model('vgg19', dev())
+        c_lv = [gd['content'], gd['content_l1']][:nlev]
+        s_lv = [gd['style'], gd['style_l1']][:nlev]
+        total, per, grad = product_closure(nst, net, cidx, sidx, c_lv, s_lv, gd['init'])
+    finally:
+        nst.PRECISION = None
+    # (i) the oracle's torch restatement on the same device with the same weights
+    onet, ocidx, osidx = O.make_vgg19(1234)
+    onet = onet.to(dev())
+    targets = [O.torch_targets(onet, ocidx, osidx, torch.from_numpy(O.prepare_img(c)).to(dev()),
+                               torch.from_numpy(O.prepare_img(s)).to(dev())) for c, s in zip(c_lv, s_lv)]
+    ototal, oper, ograd = O.torch_closure(onet, ocidx, osidx, targets, torch.from_numpy(O.prepare_img(gd['init'])).to(dev()),
+                                          WEIGHTS)
+    tol = 1e-4
+    assert abs(total - float(ototal)) / float(ototal) < tol
+    for i in range(nlev):
+        ref = np.array([float(v) for v in oper[i]])
+        np.testing.assert_allclose(per[i], ref, rtol=2e-4 if precision == 'tf32' else 5e-5)
+    assert rel(grad, ograd.cpu().numpy()) < (2e-3 if precision == 'tf32' else 1e-4)
+    # (ii) the unmodified reference on CPU (different conv arithmetic: looser)
+    assert abs(total - float(gd[f'L{nlev}_total'])) / float(gd[f'L{nlev}_total']) < 1e-3
+    np.testing.assert_allclose(per, gd[f'L{nlev}_per_level'], rtol=2e-3)
+    assert rel(grad, gd[f'L{nlev}_grad']) < 5e-3
+
+
+def test_vgg_conv4_2_is_relu4_2(seeded_vgg):
+    """the exposed 'conv4_2' map is post-ReLU because slice6 starts with an in-place ReLU."""
+    from artstyletransfer_b200 import math_utils
+    net, cidx, sidx = math_utils.prepare_model('vgg19', dev())
+    assert cidx == 4 and sidx == [0, 1, 2, 3, 5]
+    x = torch.randn(1, 3, 32, 48, device=dev()) * 50
+    out = net(x)
+    assert out._fields == ('relu1_1', 'relu2_1', 'relu3_1', 'relu4_1', 'conv4_2', 'relu5_1')
+    assert float(out.conv4_2.min()) >= 0.0
+    with pytest.raises(ValueError):
+        math_utils.prepare_model('resnet', dev())
+
+
+@pytest.mark.parametrize('opt', ['adam', 'lbfgs'])
+def test_driver_matches_reference_run(golden, seeded_vgg, opt):
+    """NeuralStyleTransfer.process end to end (async generator, executor thread, torch optimizer) vs the
+    images the reference yielded for the same seeded VGG19 and inputs: same step counters, PSNR >= 40 dB."""
+    from artstyletransfer_b200 import neural_style_transfer as nst
+    gd = golden('driver.npz')
+    content, style = O.synthetic_images(64, 96, seed=0)
+    rng = np.random.default_rng(3)
+    init = np.clip(content * 0.5 + rng.uniform(0, 1, size=content.shape) * 0.5, 0, 1).astype(np.float32)
+
+    async def run():
+        drv = nst.NeuralStyleTransfer(dev(), 'vgg19', [style], opt)
+        res = []
+        async for img, step in drv.process([content], init, 10.0, 4, 1e3, 4e5, 1e2, 'golden'):
+            res.append((np.array(img, copy=True), step))
+        return res
+
+    res = asyncio.run(run())
+    assert [s for _, s in res] == list(gd[f'{opt}_steps'])
+    assert res[-1][0].dtype == np.float32 and res[-1][0].shape == (64, 96, 3)
+    assert O.psnr(res[0][0], gd[f'{opt}_first']) >= 40.0
+    assert O.psnr(res[-1][0], gd[f'{opt}_final']) >= 40.0
+
+
+def test_adam_50_steps_psnr_vs_oracle_loop(seeded_vgg):
+    """BASELINE tolerance: final image PSNR >= 40 dB after 50 steps, product (TF32 kernels) vs the oracle's
+    torch closure driven by the same torch Adam on the same device."""
+    from artstyletransfer_b200 import math_utils, neural_style_transfer as nst
+    content, style = O.synthetic_images(64, 96, seed=1)
+    c_lv = [content, O.bicubic_resize_hwc(content, 48, 32).astype(np.float32)]
+    s_lv = [style, O.bicubic_resize_hwc(style, 48, 32).astype(np.float32)]
+    init = np.clip(content * 0.6 + np.random.default_rng(4).uniform(0, 1, size=content.shape) * 0.4, 0, 1).astype(np.float32)
+
+    async def run():
+        drv = nst.NeuralStyleTransfer(dev(), 'vgg19', s_lv, 'adam')
+        last = None
+        async for img, step in drv.process(c_lv, init, 10.0, 50, *WEIGHTS, 'psnr'):
+            last = img
+        return last
+
+    got = asyncio.run(run())
+    onet, ocidx, osidx = O.make_vgg19(1234)
+    onet = onet.to(dev())
+    targets = [O.torch_targets(onet, ocidx, osidx, torch.from_numpy(O.prepare_img(c)).to(dev()),
+                               torch.from_numpy(O.prepare_img(s)).to(dev())) for c, s in zip(c_lv, s_lv)]
+    img = torch.from_numpy(O.prepare_img(init)).to(dev()).requires_grad_(True)
+    optim = torch.optim.Adam((img,), lr=10.0)
+    for _ in range(50):
+        for g in optim.param_groups:
+            g['lr'] *= 0.999
+        optim.zero_grad()
+        _, _, grad = O.torch_closure(onet, ocidx, osidx, targets, img, WEIGHTS)
+        img.grad = grad
+        optim.step()
+    want = O.unprepare_img(img.detach().cpu().numpy())
+    assert O.psnr(got, want) >= 40.0
