@@ -6,7 +6,9 @@
 //   partial tile to the workspace and gram_finalize_kernel (gram.cu) reduces them in a fixed order.
 // Backward (K2): dF = s * D F, computed transposed, dF^T[n, c] = sum_k F[k, n] D[c, k]:  A = F tile as an
 //   MN-major operand (M = 128 spatial positions, contiguous), B = D (K-major), accumulator lane = spatial
-//   position so the epilogue's global loads/stores are 128-byte coalesced.  D stays resident in shared memory
+//   position so the epilogue's global loads/stores are 128-byte coalesced.  tcgen05 accepts a swizzled
+//   MN-major 32-bit operand only in the SWIZZLE_128B_BASE32B layout (32-byte swizzle atoms), which TMA
+//   produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (the plain 128B swizzle silently yields zeros).  D stays resident in shared memory
 //   for C <= 128 and is streamed from L2 per K chunk for C >= 256.
 //
 // Operands are fp32 in HBM.  tcgen05 kind::tf32 reads fp32 bit patterns and TRUNCATES the low 13 mantissa bits,
@@ -45,7 +47,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 row-major (rows, cols) tensor, box = (box_rows x 32 cols), 128-byte swizzle, zero OOB fill.
-static int make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+static int make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                     CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -56,7 +59,7 @@ static int make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t 
   cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu box_rows=%u", (int)r,
@@ -378,7 +381,8 @@ __global__ void __launch_bounds__(320, 1) gram_bwd_tc_kernel(const __grid_consta
           for (int k = 0; k < BK / 8; ++k) {
             const uint32_t acc = (kc > 0 || k > 0) ? 1u : 0u;
             // A: 8 channel rows (1024 B) per K step; 32-position strips 4096 B apart (LBO)
-            const uint64_t ad = umma_desc_sw128(f_base + k * 1024, 4096, 1024);
+            // SWIZZLE_128B_BASE32B: 4-row (512 B) swizzle atoms, two per K step (SBO); strips 4096 B apart (LBO)
+            const uint64_t ad = umma_desc(f_base + k * 1024, 4096, 512, 1);
             umma_tf32(d_tmem, ad, umma_desc_sw128(d_base + k * 32, 16, 1024), idesc, acc);
             if (C == 512)
               umma_tf32(d_tmem + 256, ad, umma_desc_sw128(d_base + 256 * ROW_BYTES + k * 32, 16, 1024), idesc, acc);
@@ -538,7 +542,8 @@ static int launch_bwd(const float* D, const float* F, int64_t HW, float scale, c
                       int accumulate, int num_sms, cudaStream_t stream) {
   using Cfg = BwdCfg<C>;
   CUtensorMap tmF, tmD;
-  int rc = make_tmap(&tmF, F, C, HW, 32);
+  // MN-major fp32 operand: tcgen05 only accepts the 128B swizzle with 32-byte atoms (SWIZZLE_128B_BASE32B)
+  int rc = make_tmap(&tmF, F, C, HW, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc != AST_OK) return rc;
   rc = make_tmap(&tmD, D, C, C, Cfg::kDBoxRows);
   if (rc != AST_OK) return rc;

@@ -99,10 +99,22 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA (tcgen05.mma) ----------------------------------------------------------------------------------
-// Shared-memory matrix descriptor, SWIZZLE_128B, Blackwell version bit set.
-//   K-major operand  (rows of 128 B = 32 fp32 of K): SBO = 1024 B between 8-row groups, LBO unused (1).
-//   MN-major operand (rows of 128 B = 32 fp32 of M/N, one row per K index): LBO = byte distance between
-//   consecutive 32-element M/N strips, SBO = 1024 B between 8-K groups.
+// Shared-memory matrix descriptors (Blackwell version bit set).
+//   K-major operand, SWIZZLE_128B: rows of 128 B = 32 fp32 of K; SBO = 1024 B between 8-row groups, LBO unused.
+//   MN-major fp32 operand, SWIZZLE_128B_BASE32B: rows of 128 B = 32 fp32 of M/N, one row per K index;
+//   LBO = bytes between consecutive 32-element M/N strips, SBO = 512 B between 4-row swizzle atoms along K.
+// layout_type: 2 = SWIZZLE_128B (16-byte swizzle atom), 1 = SWIZZLE_128B_BASE32B (32-byte atom; the only
+// swizzled layout tcgen05 accepts for an MN-major 32-bit operand: rows of 128 B, 4 K-rows per 512-byte atom).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (sm_100)
+  d |= (uint64_t)(layout_type & 7u) << 61;
+  return d;
+}
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);

@@ -77,7 +77,8 @@ def test_bicubic_half_and_adjoint(shape):
     y = ops.bicubic_half(xd)
     ref = O.bicubic_down2x(x.numpy())
     assert tuple(y.shape) == ref.shape
-    assert np.abs(y.detach().cpu().numpy() - ref).max() < 6e-5          # |x| ~ 60..250: a few fp32 ulps
+    # |x| ~ 60..250; the general-ratio path forms its weights in fp32 like torch does: a few 1e-7 relative
+    assert np.abs(y.detach().cpu().numpy() - ref).max() < 2e-4
     u = torch.randn(y.shape, generator=g)
     (y * u.to(dev())).sum().backward()
     ref_adj = O.bicubic_resize_chw_adjoint(u.numpy(), shape[2], shape[3])

