@@ -43,7 +43,7 @@ __device__ __forceinline__ void load_rows_k32(const float* __restrict__ F, int64
 }
 
 __global__ void __launch_bounds__(256) gram_fp32_fwd_kernel(const float* __restrict__ F, int C, int64_t HW,
-                                                           int64_t k_per_split, int vec_ok,
+                                                           int64_t ld, int64_t k_per_split, int vec_ok,
                                                            float* __restrict__ partials) {
   __shared__ float As[SG_T][SG_PITCH];
   __shared__ float Bs[SG_T][SG_PITCH];
@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(256) gram_fp32_fwd_kernel(const float* __restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int64_t k0 = kbeg; k0 < kend; k0 += SG_K) {
-    load_rows_k32(F, HW, ti * SG_T, k0, kend, vec_ok, As);
-    if (ti != tj) load_rows_k32(F, HW, tj * SG_T, k0, kend, vec_ok, Bs);
+    load_rows_k32(F, ld, ti * SG_T, k0, kend, vec_ok, As);
+    if (ti != tj) load_rows_k32(F, ld, tj * SG_T, k0, kend, vec_ok, Bs);
     __syncthreads();
     float(*Bp)[SG_PITCH] = (ti != tj) ? Bs : As;
 #pragma unroll 8
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) gram_fp32_fwd_kernel(const float* __restr
 
 // exact fp32 path, backward: dF[c, n] (+)= scale * sum_k D[c, k] F[k, n];  64 (c) x 64 (n) tile per CTA.
 __global__ void __launch_bounds__(256) gram_fp32_bwd_kernel(const float* __restrict__ D, const float* __restrict__ F,
-                                                           int C, int64_t HW, float scale,
+                                                           int C, int64_t HW, int64_t ld, float scale,
                                                            const float* __restrict__ gscale, float* __restrict__ dF,
                                                            int accumulate, int vec_ok) {
   if (gscale) scale *= __ldg(gscale);
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) gram_fp32_bwd_kernel(const float* __restr
       const int slot = threadIdx.x + it * 256;
       const int kk = slot >> 4, nq = slot & 15;
       const int64_t n = n0 + 4 * nq;
-      const float* p = F + (size_t)(k0 + kk) * HW + n;
+      const float* p = F + (size_t)(k0 + kk) * ld + n;
       float4 v;
       if (vec_ok && n + 3 < HW) {
         v = __ldg(reinterpret_cast<const float4*>(p));
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) gram_fp32_bwd_kernel(const float* __restr
     for (int j = 0; j < 4; ++j) {
       const int64_t n = n0 + tx + 16 * j;
       if (n < HW) {
-        float* o = dF + (size_t)(c0 + ty * 4 + i) * HW + n;
+        float* o = dF + (size_t)(c0 + ty * 4 + i) * ld + n;
         const float v = scale * acc[i][j];
         *o = accumulate ? *o + v : v;
       }
@@ -280,11 +280,12 @@ extern "C" size_t ast_gram_workspace_bytes(int C, int64_t HW) {
   return kGramWsHeaderBytes + parts * sizeof(float);
 }
 
-extern "C" int ast_gram_mse_fwd(const float* F, int C, int64_t HW, float scale, const float* A, float* out,
-                                float* loss, void* ws, size_t ws_bytes, int precision, void* stream_) {
+extern "C" int ast_gram_mse_fwd(const float* F, int C, int64_t HW, int64_t ld, float scale, const float* A,
+                                float* out, float* loss, void* ws, size_t ws_bytes, int precision, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   AST_REQUIRE(F && out && ws, AST_ERR_INVALID, "ast_gram_mse_fwd: null pointer");
   AST_REQUIRE(C > 0 && HW > 0, AST_ERR_INVALID, "ast_gram_mse_fwd: bad shape C=%d HW=%lld", C, (long long)HW);
+  AST_REQUIRE(ld >= HW, AST_ERR_INVALID, "ast_gram_mse_fwd: row pitch %lld < HW %lld", (long long)ld, (long long)HW);
   AST_REQUIRE(C % SG_T == 0, AST_ERR_UNSUPPORTED, "ast_gram_mse_fwd: C must be a multiple of 64 (got %d)", C);
   AST_REQUIRE(is16(out) && (!A || is16(A)) && is16(ws), AST_ERR_INVALID, "ast_gram_mse_fwd: out/A/ws must be 16-byte aligned");
   AST_REQUIRE(precision == AST_PREC_TF32 || precision == AST_PREC_FP32, AST_ERR_INVALID, "ast_gram_mse_fwd: bad precision %d", precision);
@@ -293,21 +294,21 @@ extern "C" int ast_gram_mse_fwd(const float* F, int C, int64_t HW, float scale, 
   float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kGramWsHeaderBytes);
   GramPlan plan;
   if (precision == AST_PREC_TF32) {
-    AST_REQUIRE(gram_tc_supported(C, HW, F), AST_ERR_UNSUPPORTED,
-                "ast_gram_mse_fwd: TF32 path needs C in {64,128,256,512}, HW %% 4 == 0 and 16-byte aligned F "
-                "(C=%d HW=%lld); use AST_PREC_FP32", C, (long long)HW);
+    AST_REQUIRE(gram_tc_supported(C, HW, F) && (ld % 4 == 0), AST_ERR_UNSUPPORTED,
+                "ast_gram_mse_fwd: TF32 path needs C in {64,128,256,512}, HW %% 4 == 0, ld %% 4 == 0 and 16-byte "
+                "aligned F (C=%d HW=%lld ld=%lld); use AST_PREC_FP32", C, (long long)HW, (long long)ld);
     const int sms = cached_num_sms();
     gram_tc_plan(C, HW, sms < 148 ? sms : 148, &plan);
-    int rc = gram_tc_fwd(F, C, HW, partials, plan, sms, stream);
+    int rc = gram_tc_fwd(F, C, HW, ld, partials, plan, sms, stream);
     if (rc != AST_OK) return rc;
     return launch_finalize(plan, partials, 1, scale, A, out, loss, ws, stream);
   }
   const int splits = fp32_splits(C, HW);
   int64_t kps = (HW + splits - 1) / splits;
   kps = (kps + SG_K - 1) / SG_K * SG_K;
-  const int vec_ok = is16(F) && (HW % 4 == 0);
+  const int vec_ok = is16(F) && (ld % 4 == 0);
   dim3 grid((C / SG_T) * (C / SG_T), splits);
-  gram_fp32_fwd_kernel<<<grid, 256, 0, stream>>>(F, C, HW, kps, vec_ok, partials);
+  gram_fp32_fwd_kernel<<<grid, 256, 0, stream>>>(F, C, HW, ld, kps, vec_ok, partials);
   int rc = check_launch("gram_fp32_fwd");
   if (rc != AST_OK) return rc;
   plan.C = C; plan.TR = C; plan.n_tiles = 1;
@@ -329,21 +330,22 @@ extern "C" int ast_gram_finalize(const float* G_raw, int C, float scale, const f
   return launch_finalize(plan, G_raw, 0, scale, A, out, loss, ws, (cudaStream_t)stream);
 }
 
-extern "C" int ast_gram_bwd(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale,
-                            float* dF, int accumulate, int precision, void* stream_) {
+extern "C" int ast_gram_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, float scale,
+                            const float* gscale, float* dF, int accumulate, int precision, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   AST_REQUIRE(D && F && dF, AST_ERR_INVALID, "ast_gram_bwd: null pointer");
   AST_REQUIRE(C > 0 && HW > 0, AST_ERR_INVALID, "ast_gram_bwd: bad shape C=%d HW=%lld", C, (long long)HW);
+  AST_REQUIRE(ld >= HW, AST_ERR_INVALID, "ast_gram_bwd: row pitch %lld < HW %lld", (long long)ld, (long long)HW);
   AST_REQUIRE(C % SG_T == 0, AST_ERR_UNSUPPORTED, "ast_gram_bwd: C must be a multiple of 64 (got %d)", C);
   AST_REQUIRE(precision == AST_PREC_TF32 || precision == AST_PREC_FP32, AST_ERR_INVALID, "ast_gram_bwd: bad precision %d", precision);
   if (precision == AST_PREC_TF32) {
-    AST_REQUIRE(gram_tc_supported(C, HW, F) && is16(dF) && is16(D), AST_ERR_UNSUPPORTED,
-                "ast_gram_bwd: TF32 path needs C in {64,128,256,512}, HW %% 4 == 0 and 16-byte aligned pointers "
-                "(C=%d HW=%lld); use AST_PREC_FP32", C, (long long)HW);
-    return gram_tc_bwd(D, F, C, HW, scale, gscale, dF, accumulate, cached_num_sms(), stream);
+    AST_REQUIRE(gram_tc_supported(C, HW, F) && (ld % 4 == 0) && is16(D), AST_ERR_UNSUPPORTED,
+                "ast_gram_bwd: TF32 path needs C in {64,128,256,512}, HW %% 4 == 0, ld %% 4 == 0 and 16-byte aligned "
+                "F/D (C=%d HW=%lld ld=%lld); use AST_PREC_FP32", C, (long long)HW, (long long)ld);
+    return gram_tc_bwd(D, F, C, HW, ld, scale, gscale, dF, accumulate, cached_num_sms(), stream);
   }
-  const int vec_ok = is16(F) && (HW % 4 == 0);
+  const int vec_ok = is16(F) && (ld % 4 == 0);
   dim3 grid((unsigned)((HW + SG_T - 1) / SG_T), C / SG_T);
-  gram_fp32_bwd_kernel<<<grid, 256, 0, stream>>>(D, F, C, HW, scale, gscale, dF, accumulate, vec_ok);
+  gram_fp32_bwd_kernel<<<grid, 256, 0, stream>>>(D, F, C, HW, ld, scale, gscale, dF, accumulate, vec_ok);
   return check_launch("gram_fp32_bwd");
 }

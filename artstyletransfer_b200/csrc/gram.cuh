@@ -31,9 +31,9 @@ static_assert(sizeof(ReduceWs) <= kGramWsHeaderBytes, "reduce header too small")
 bool gram_tc_supported(int C, int64_t HW, const void* F);
 // Plans the split-K decomposition for `num_sms` SMs (no device access).
 void gram_tc_plan(int C, int64_t HW, int num_sms, GramPlan* plan);
-int gram_tc_fwd(const float* F, int C, int64_t HW, float* partials, const GramPlan& plan, int num_sms,
+int gram_tc_fwd(const float* F, int C, int64_t HW, int64_t ld, float* partials, const GramPlan& plan, int num_sms,
                 cudaStream_t stream);
-int gram_tc_bwd(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale, float* dF,
-                int accumulate, int num_sms, cudaStream_t stream);
+int gram_tc_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, float scale, const float* gscale,
+                float* dF, int accumulate, int num_sms, cudaStream_t stream);
 
 }  // namespace ast

@@ -47,15 +47,15 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 row-major (rows, cols) tensor, box = (box_rows x 32 cols), 128-byte swizzle, zero OOB fill.
-static int make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                     CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+static int make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t pitch,
+                     uint32_t box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
     return AST_ERR_CUDA;
   }
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * sizeof(float)};
+  cuuint64_t gstride[1] = {pitch * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(192, 1) gram_fwd_tc_kernel(const __grid_consta
 // ------------------------------------------------------------------------------------------------------
 struct BwdParams {
   int64_t HW;
+  int64_t ld;
   int n_tiles;       // ceil(HW / 128)
   float scale;
   const float* gscale;   // nullable device scalar multiplied into scale
@@ -428,13 +429,13 @@ __global__ void __launch_bounds__(320, 1) gram_bwd_tc_kernel(const __grid_consta
         tmem_ld_x32(lane_addr + b * C + g * 32, v);
         tmem_ld_wait();
         if (n < P.HW) {
-          float* o = out + (size_t)(g * 32) * P.HW;
+          float* o = out + (size_t)(g * 32) * P.ld;
           if (P.accumulate) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[(size_t)j * P.HW] += scale * __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) o[(size_t)j * P.ld] += scale * __uint_as_float(v[j]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[(size_t)j * P.HW] = scale * __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) o[(size_t)j * P.ld] = scale * __uint_as_float(v[j]);
           }
         }
       }
@@ -495,10 +496,11 @@ void gram_tc_plan(int C, int64_t HW, int num_sms, GramPlan* plan) {
 }
 
 template <int C>
-static int launch_fwd(const float* F, int64_t HW, float* partials, const GramPlan& plan, cudaStream_t stream) {
+static int launch_fwd(const float* F, int64_t HW, int64_t ld, float* partials, const GramPlan& plan,
+                      cudaStream_t stream) {
   using Cfg = FwdCfg<C>;
   CUtensorMap tmap;
-  int rc = make_tmap(&tmap, F, C, HW, Cfg::kBoxRows);
+  int rc = make_tmap(&tmap, F, C, HW, ld, Cfg::kBoxRows);
   if (rc != AST_OK) return rc;
   FwdParams P;
   P.HW = HW;
@@ -524,31 +526,32 @@ static int launch_fwd(const float* F, int64_t HW, float* partials, const GramPla
   return check_launch("gram_fwd_tc");
 }
 
-int gram_tc_fwd(const float* F, int C, int64_t HW, float* partials, const GramPlan& plan, int num_sms,
+int gram_tc_fwd(const float* F, int C, int64_t HW, int64_t ld, float* partials, const GramPlan& plan, int num_sms,
                 cudaStream_t stream) {
   (void)num_sms;
   switch (C) {
-    case 64: return launch_fwd<64>(F, HW, partials, plan, stream);
-    case 128: return launch_fwd<128>(F, HW, partials, plan, stream);
-    case 256: return launch_fwd<256>(F, HW, partials, plan, stream);
-    case 512: return launch_fwd<512>(F, HW, partials, plan, stream);
+    case 64: return launch_fwd<64>(F, HW, ld, partials, plan, stream);
+    case 128: return launch_fwd<128>(F, HW, ld, partials, plan, stream);
+    case 256: return launch_fwd<256>(F, HW, ld, partials, plan, stream);
+    case 512: return launch_fwd<512>(F, HW, ld, partials, plan, stream);
   }
   set_error("gram_tc_fwd: unsupported C=%d", C);
   return AST_ERR_UNSUPPORTED;
 }
 
 template <int C>
-static int launch_bwd(const float* D, const float* F, int64_t HW, float scale, const float* gscale, float* dF,
-                      int accumulate, int num_sms, cudaStream_t stream) {
+static int launch_bwd(const float* D, const float* F, int64_t HW, int64_t ld, float scale, const float* gscale,
+                      float* dF, int accumulate, int num_sms, cudaStream_t stream) {
   using Cfg = BwdCfg<C>;
   CUtensorMap tmF, tmD;
   // MN-major fp32 operand: tcgen05 only accepts the 128B swizzle with 32-byte atoms (SWIZZLE_128B_BASE32B)
-  int rc = make_tmap(&tmF, F, C, HW, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  int rc = make_tmap(&tmF, F, C, HW, ld, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc != AST_OK) return rc;
-  rc = make_tmap(&tmD, D, C, C, Cfg::kDBoxRows);
+  rc = make_tmap(&tmD, D, C, C, C, Cfg::kDBoxRows);
   if (rc != AST_OK) return rc;
   BwdParams P;
   P.HW = HW;
+  P.ld = ld;
   P.n_tiles = (int)((HW + 127) / 128);
   P.scale = scale;
   P.gscale = gscale;
@@ -564,13 +567,13 @@ static int launch_bwd(const float* D, const float* F, int64_t HW, float scale, c
   return check_launch("gram_bwd_tc");
 }
 
-int gram_tc_bwd(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale, float* dF,
-                int accumulate, int num_sms, cudaStream_t stream) {
+int gram_tc_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, float scale, const float* gscale,
+                float* dF, int accumulate, int num_sms, cudaStream_t stream) {
   switch (C) {
-    case 64: return launch_bwd<64>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
-    case 128: return launch_bwd<128>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
-    case 256: return launch_bwd<256>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
-    case 512: return launch_bwd<512>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
+    case 64: return launch_bwd<64>(D, F, HW, ld, scale, gscale, dF, accumulate, num_sms, stream);
+    case 128: return launch_bwd<128>(D, F, HW, ld, scale, gscale, dF, accumulate, num_sms, stream);
+    case 256: return launch_bwd<256>(D, F, HW, ld, scale, gscale, dF, accumulate, num_sms, stream);
+    case 512: return launch_bwd<512>(D, F, HW, ld, scale, gscale, dF, accumulate, num_sms, stream);
   }
   set_error("gram_tc_bwd: unsupported C=%d", C);
   return AST_ERR_UNSUPPORTED;

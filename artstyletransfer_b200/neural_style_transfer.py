@@ -91,7 +91,8 @@ class LossBuilder:
             del style_rep_builder
         self.__target_grams = [g[0].detach().contiguous() for g in self.__target_style_representation]
         self.__wss = ops.LevelWorkspaces()
-        self.shard = None           # set by parallel.shard_loss_builders for row-band sharded levels
+        self.shard = None                   # set by parallel.maybe_shard for row-band sharded levels
+        self.replicated_rank0_only = False  # sharding on, level not shardable: ranks != 0 evaluate without grad
 
     @property
     def target_content_representation(self):
@@ -104,6 +105,9 @@ class LossBuilder:
     def build(self, optimizing_img):
         if self.shard is not None:
             return self.shard.build(optimizing_img)
+        if self.replicated_rank0_only and torch.is_grad_enabled():
+            with torch.no_grad():
+                return self.build(optimizing_img)
         feats = self.__neural_net(optimizing_img)
         cfg = (self.__target_content_representation, self.__target_grams,
                (self.__content_weight, self.__style_weight, self.__tv_weight), self.__wss, ops._prec(PRECISION))
@@ -111,6 +115,94 @@ class LossBuilder:
             cfg, optimizing_img, feats[self.__content_feature_maps_index],
             *[feats[k] for k in self.__style_feature_maps_indices])
         return total_loss, content_loss, style_loss, tv_loss
+
+
+class _Job:
+    """What NeuralStyleTransfer.process sets up (:124-147) and its closure (:152-202): the leaf image, the torch
+    optimizer, one LossBuilder per pyramid level.  Split out so that bench.py can time closures directly."""
+
+    def __init__(self, device, model_name, style_imgs, optimizer_name, content_imgs, init_img, lr_start,
+                 content_weight, style_weight, tv_weight, init_img_name):
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise RuntimeError('artstyletransfer_b200 runs the Gatys-loss path on sm_100a CUDA only; '
+                               f'got device {device} (no CPU fallback)')
+        if optimizer_name not in ('adam', 'lbfgs'):
+            raise RuntimeError("Unknown optimizer")
+        neural_net, content_feature_maps_index, style_feature_maps_indices = \
+            math_utils.prepare_model(model_name, device)
+        if VERBOSE:
+            print(f'Using {model_name} in the optimization procedure.')
+        init_img = prepare_img(init_img, device)
+        # we are tuning optimizing_img's pixels! (that's why requires_grad=True)
+        self.optimizing_img = Variable(init_img, requires_grad=True)
+        if optimizer_name == 'adam':
+            self.optimizer = Adam((self.optimizing_img,), lr=lr_start)
+        else:
+            self.optimizer = LBFGS((self.optimizing_img,), max_iter=1, line_search_fn='strong_wolfe', lr=lr_start)
+        self.loss_builders = []
+        for content_img, style_img in zip(content_imgs, style_imgs):
+            content_img = prepare_img(content_img, device)
+            style_img = prepare_img(style_img, device)
+            self.loss_builders.append(LossBuilder(content_feature_maps_index, style_feature_maps_indices, content_img,
+                                                  style_img, neural_net, content_weight, style_weight, tv_weight))
+        self.sharded_levels = _parallel.maybe_shard(self.loss_builders, self.optimizing_img, neural_net,
+                                                    content_feature_maps_index, style_feature_maps_indices,
+                                                    (content_weight, style_weight, tv_weight))
+        self.step = 0
+        self.optimizer_name = optimizer_name
+        self.init_img_name = init_img_name
+        self.weights = (content_weight, style_weight, tv_weight)
+
+    def closure(self):
+        try:
+            optimizer, optimizing_img, loss_builders = self.optimizer, self.optimizing_img, self.loss_builders
+            content_weight, style_weight, tv_weight = self.weights
+            # learning rate schedule (:155-159)
+            lr = 0
+            for g in optimizer.param_groups:
+                g['lr'] *= 0.999
+                lr = g['lr']
+            if torch.is_grad_enabled():
+                optimizer.zero_grad()
+            if VERBOSE:
+                print(f"new lr = {lr}")
+                print(f'{self.optimizer_name} | processing image: {self.init_img_name} | iteration: {self.step:03} :')
+            optimizing_img_levels = None
+            total_loss = None
+            for i in range(len(loss_builders)):
+                # lower resolutions of optimizing_img: chained bicubic 2x down (:168-176)
+                if i == 0:
+                    optimizing_img_levels = [optimizing_img]
+                else:
+                    optimizing_img_levels.append(ops.bicubic_half(optimizing_img_levels[i - 1]))
+                total_loss_l, content_loss, style_loss, tv_loss = loss_builders[i].build(optimizing_img_levels[i])
+                if total_loss is None:
+                    total_loss = total_loss_l
+                else:
+                    previous_loss_importance = 1.0
+                    total_loss = previous_loss_importance * total_loss + total_loss_l
+                if VERBOSE:
+                    with torch.no_grad():
+                        print(f' - level {i} | level loss={total_loss_l.item():.3e}, '
+                              f'content_loss={content_weight * content_loss.item():.3e}, '
+                              f'style loss={style_weight * style_loss:.3e}, '
+                              f'tv loss={tv_weight * tv_loss.item():.3e}')
+            if total_loss.requires_grad:
+                total_loss.backward()
+            if torch.is_grad_enabled():
+                _parallel.sync_image_grad(optimizing_img)
+            if VERBOSE:
+                with torch.no_grad():
+                    print(f'{self.optimizer_name} | total loss={total_loss.item():.3e}')
+            self.step += 1
+            return total_loss
+        except:
+            traceback.print_exc()
+            raise
+
+    def optimizer_step(self):
+        return self.optimizer.step(self.closure)
 
 
 class NeuralStyleTransfer:
@@ -123,86 +215,12 @@ class NeuralStyleTransfer:
 
     async def process(self, content_imgs, init_img, lr_start, iters_num, content_weight, style_weight, tv_weight,
                       init_img_name):
-        device = torch.device(self.__device)
-        if device.type != 'cuda':
-            raise RuntimeError('artstyletransfer_b200 runs the Gatys-loss path on sm_100a CUDA only; '
-                               f'got device {device} (no CPU fallback)')
-        neural_net, content_feature_maps_index, style_feature_maps_indices = \
-            math_utils.prepare_model(self.__model_name, device)
-        if VERBOSE:
-            print(f'Using {self.__model_name} in the optimization procedure.')
-
-        init_img = prepare_img(init_img, device)
-        # we are tuning optimizing_img's pixels! (that's why requires_grad=True)
-        optimizing_img = Variable(init_img, requires_grad=True)
-
-        if self.__optimizer_name == 'adam':
-            optimizer = Adam((optimizing_img,), lr=lr_start)
-        elif self.__optimizer_name == 'lbfgs':
-            optimizer = LBFGS((optimizing_img,), max_iter=1, line_search_fn='strong_wolfe', lr=lr_start)
-        else:
-            raise RuntimeError("Unknown optimizer")
-
-        loss_builders = []
-        for content_img, style_img in zip(content_imgs, self.__style_imgs):
-            content_img = prepare_img(content_img, device)
-            style_img = prepare_img(style_img, device)
-            loss_builders.append(LossBuilder(content_feature_maps_index, style_feature_maps_indices, content_img,
-                                             style_img, neural_net, content_weight, style_weight, tv_weight))
-        _parallel.maybe_shard(loss_builders, optimizing_img, neural_net, content_feature_maps_index,
-                              style_feature_maps_indices, (content_weight, style_weight, tv_weight))
-
-        step = 0
-
-        def optimizer_step_callback():
-            try:
-                # learning rate schedule (:155-159)
-                lr = 0
-                for g in optimizer.param_groups:
-                    g['lr'] *= 0.999
-                    lr = g['lr']
-                nonlocal step
-                if torch.is_grad_enabled():
-                    optimizer.zero_grad()
-                if VERBOSE:
-                    print(f"new lr = {lr}")
-                    print(f'{self.__optimizer_name} | processing image: {init_img_name} | iteration: {step:03} :')
-                optimizing_img_levels = None
-                total_loss = None
-                for i in range(len(loss_builders)):
-                    # lower resolutions of optimizing_img: chained bicubic 2x down (:168-176)
-                    if i == 0:
-                        optimizing_img_levels = [optimizing_img]
-                    else:
-                        optimizing_img_levels.append(ops.bicubic_half(optimizing_img_levels[i - 1]))
-                    total_loss_l, content_loss, style_loss, tv_loss = loss_builders[i].build(optimizing_img_levels[i])
-                    if total_loss is None:
-                        total_loss = total_loss_l
-                    else:
-                        previous_loss_importance = 1.0
-                        total_loss = previous_loss_importance * total_loss + total_loss_l
-                    if VERBOSE:
-                        with torch.no_grad():
-                            print(f' - level {i} | level loss={total_loss_l.item():.3e}, '
-                                  f'content_loss={content_weight * content_loss.item():.3e}, '
-                                  f'style loss={style_weight * style_loss:.3e}, '
-                                  f'tv loss={tv_weight * tv_loss.item():.3e}')
-                if total_loss.requires_grad:
-                    total_loss.backward()
-                    _parallel.sync_image_grad(optimizing_img)
-                if VERBOSE:
-                    with torch.no_grad():
-                        print(f'{self.__optimizer_name} | total loss={total_loss.item():.3e}')
-                step += 1
-                return total_loss
-            except:
-                traceback.print_exc()
-                raise
-
-        # the main optimization loop (:205-208)
-        while step < iters_num:
-            await asyncio.get_running_loop().run_in_executor(None, optimizer.step, optimizer_step_callback)
-            yield unprepare_img(optimizing_img), step
+        job = _Job(self.__device, self.__model_name, self.__style_imgs, self.__optimizer_name, content_imgs, init_img,
+                   lr_start, content_weight, style_weight, tv_weight, init_img_name)
+        # the main optimization loop (:205-208): optimizer.step runs on the default executor's worker thread
+        while job.step < iters_num:
+            await asyncio.get_running_loop().run_in_executor(None, job.optimizer_step)
+            yield unprepare_img(job.optimizing_img), job.step
 
 
 def _device():
@@ -379,8 +397,9 @@ def prepare_img(img, device):
 
 
 def unprepare_img(img: Tensor):
-    """ Reverse of prepare_img (:388-393): (1,3,H,W) device tensor -> HxWx3 float32 numpy on the host """
-    dump_img = img.detach().permute([0, 2, 3, 1]).squeeze(0).to("cpu").numpy()
-    dump_img += np.array(IMAGENET_MEAN_255).reshape((1, 1, 3))
-    dump_img = dump_img.astype(np.float32) / 255
-    return dump_img
+    """ Reverse of prepare_img (:388-393): (1,3,H,W) tensor -> HxWx3 float32 numpy on the host.
+    The mean add and the /255 run on the device, then ONE contiguous device->host copy of the HWC image. """
+    t = img.detach()
+    mean = torch.tensor(IMAGENET_MEAN_255, dtype=torch.float32, device=t.device).view(1, 3, 1, 1)
+    hwc = ((t + mean) / 255).permute([0, 2, 3, 1]).squeeze(0).contiguous()
+    return hwc.to("cpu").numpy()

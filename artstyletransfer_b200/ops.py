@@ -42,6 +42,54 @@ def _stream(dev: torch.device) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+class KernelStats:
+    """Optional instrumentation for bench.py: counts this library's kernel launches and, when `timing` is on,
+    brackets every C-ABI call with CUDA events on the launching stream (resolved after a synchronize)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.timing = False
+        self.launches = 0
+        self.events = []      # (key, start_event, stop_event)
+
+    def reset(self, enabled=True, timing=False):
+        self.enabled, self.timing, self.launches, self.events = enabled, timing, 0, []
+
+    def summary(self):
+        out = {}
+        for key, a, b in self.events:
+            d = out.setdefault(key, [0, 0.0])
+            d[0] += 1
+            d[1] += a.elapsed_time(b)
+        return {k: {'calls': v[0], 'ms_total': v[1], 'ms_avg': v[1] / v[0]} for k, v in out.items()}
+
+
+STATS = KernelStats()
+
+# kernels launched per C-ABI entry point
+_KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_finalize': 1, 'ast_gram_bwd': 1, 'ast_mse_fwd': 1, 'ast_mse_bwd': 1,
+                     'ast_tv_fwd': 1, 'ast_tv_bwd': 1, 'ast_level_combine': 1, 'ast_bicubic_down2x': 1,
+                     'ast_bicubic_down2x_adj': 1, 'ast_bicubic_resize': 1, 'ast_bicubic_resize_adj': 1,
+                     'ast_noise_init': 1}
+
+
+def _launch(dev: torch.device, key, name: str, *args) -> None:
+    """Call an entry point on `dev`'s current stream (last ABI argument)."""
+    st = torch.cuda.current_stream(dev)
+    with _on(dev):
+        if STATS.enabled:
+            STATS.launches += _KERNELS_PER_CALL[name]
+            if STATS.timing:
+                a = torch.cuda.Event(enable_timing=True)
+                b = torch.cuda.Event(enable_timing=True)
+                a.record(st)
+                L.call(name, *args, st.cuda_stream)
+                b.record(st)
+                STATS.events.append((key, a, b))
+                return
+        L.call(name, *args, st.cuda_stream)
+
+
 class _on:
     """Make `dev` current for the duration of a launch (the C ABI launches on the current device)."""
     __slots__ = ('dev', 'prev')
@@ -104,29 +152,27 @@ def _thread_ws(kind: str, nbytes: int, device: torch.device) -> Workspace:
 # raw launches
 # ------------------------------------------------------------------------------------------------------
 def gram_mse_fwd(feat: torch.Tensor, C: int, HW: int, scale: float, target: Optional[torch.Tensor],
-                 out: torch.Tensor, loss: Optional[torch.Tensor], ws: Workspace, precision: int) -> None:
-    dev = feat.device
-    with _on(dev):
-        L.call('ast_gram_mse_fwd', feat.data_ptr(), C, HW, scale,
-               target.data_ptr() if target is not None else None, out.data_ptr(),
-               loss.data_ptr() if loss is not None else None, ws.ptr, ws.nbytes, precision, _stream(dev))
+                 out: torch.Tensor, loss: Optional[torch.Tensor], ws: Workspace, precision: int,
+                 ld: Optional[int] = None, offset: int = 0) -> None:
+    """feat: base tensor; the (C, HW) operand starts `offset` elements in and has row pitch `ld` (default HW)."""
+    _launch(feat.device, ('gram_fwd', C, HW, precision), 'ast_gram_mse_fwd', feat.data_ptr() + 4 * offset, C, HW,
+            HW if ld is None else ld, scale,
+            target.data_ptr() if target is not None else None, out.data_ptr(),
+            loss.data_ptr() if loss is not None else None, ws.ptr, ws.nbytes, precision)
 
 
 def gram_finalize(g_raw: torch.Tensor, C: int, scale: float, target: Optional[torch.Tensor], out: torch.Tensor,
                   loss: Optional[torch.Tensor], ws: Workspace) -> None:
-    dev = g_raw.device
-    with _on(dev):
-        L.call('ast_gram_finalize', g_raw.data_ptr(), C, scale, target.data_ptr() if target is not None else None,
-               out.data_ptr(), loss.data_ptr() if loss is not None else None, ws.ptr, ws.nbytes, _stream(dev))
+    _launch(g_raw.device, ('gram_finalize', C), 'ast_gram_finalize', g_raw.data_ptr(), C, scale,
+            target.data_ptr() if target is not None else None, out.data_ptr(),
+            loss.data_ptr() if loss is not None else None, ws.ptr, ws.nbytes)
 
 
 def gram_bwd(D: torch.Tensor, feat: torch.Tensor, C: int, HW: int, scale: float, gscale: Optional[torch.Tensor],
-             dF: torch.Tensor, accumulate: bool, precision: int) -> None:
-    dev = feat.device
-    with _on(dev):
-        L.call('ast_gram_bwd', D.data_ptr(), feat.data_ptr(), C, HW, scale,
-               gscale.data_ptr() if gscale is not None else None, dF.data_ptr(), int(accumulate), precision,
-               _stream(dev))
+             dF: torch.Tensor, accumulate: bool, precision: int, ld: Optional[int] = None, offset: int = 0) -> None:
+    _launch(feat.device, ('gram_bwd', C, HW, precision), 'ast_gram_bwd', D.data_ptr(), feat.data_ptr() + 4 * offset, C,
+            HW, HW if ld is None else ld, scale, gscale.data_ptr() if gscale is not None else None,
+            dF.data_ptr() + 4 * offset, int(accumulate), precision)
 
 
 def _gscale(g: Optional[torch.Tensor], dev: torch.device) -> Optional[torch.Tensor]:
@@ -210,17 +256,13 @@ class StyleLossFn(torch.autograd.Function):
 # ContentLoss: mean((T - X)^2)   (neural_style_transfer.py:95)
 # ------------------------------------------------------------------------------------------------------
 def mse_fwd(x, t, scale, loss, ws):
-    dev = x.device
-    with _on(dev):
-        L.call('ast_mse_fwd', x.data_ptr(), t.data_ptr(), x.numel(), scale, loss.data_ptr(), ws.ptr, ws.nbytes,
-               _stream(dev))
+    _launch(x.device, ('mse_fwd', x.numel()), 'ast_mse_fwd', x.data_ptr(), t.data_ptr(), x.numel(), scale,
+            loss.data_ptr(), ws.ptr, ws.nbytes)
 
 
 def mse_bwd(x, t, scale, gscale, dx, accumulate):
-    dev = x.device
-    with _on(dev):
-        L.call('ast_mse_bwd', x.data_ptr(), t.data_ptr(), x.numel(), scale,
-               gscale.data_ptr() if gscale is not None else None, dx.data_ptr(), int(accumulate), _stream(dev))
+    _launch(x.device, ('mse_bwd', x.numel()), 'ast_mse_bwd', x.data_ptr(), t.data_ptr(), x.numel(), scale,
+            gscale.data_ptr() if gscale is not None else None, dx.data_ptr(), int(accumulate))
 
 
 class ContentLossFn(torch.autograd.Function):
@@ -248,11 +290,9 @@ class ContentLossFn(torch.autograd.Function):
 # total variation (math_utils.py:37-41)
 # ------------------------------------------------------------------------------------------------------
 def tv_fwd(y, sums2, tv, ws):
-    dev = y.device
     c = y.numel() // (y.shape[-2] * y.shape[-1])
-    with _on(dev):
-        L.call('ast_tv_fwd', y.data_ptr(), c, y.shape[-2], y.shape[-1], sums2.data_ptr(),
-               tv.data_ptr() if tv is not None else None, ws.ptr, ws.nbytes, _stream(dev))
+    _launch(y.device, ('tv_fwd', y.numel()), 'ast_tv_fwd', y.data_ptr(), c, y.shape[-2], y.shape[-1], sums2.data_ptr(),
+            tv.data_ptr() if tv is not None else None, ws.ptr, ws.nbytes)
 
 
 def tv_bwd(y, sums2, weight, gscale, dy, accumulate):
@@ -260,10 +300,9 @@ def tv_bwd(y, sums2, weight, gscale, dy, accumulate):
     h, w = y.shape[-2], y.shape[-1]
     c = y.numel() // (h * w)
     nx, ny = float(c) * h * (w - 1), float(c) * (h - 1) * w
-    with _on(dev):
-        L.call('ast_tv_bwd', y.data_ptr(), c, h, w, sums2.data_ptr(), 2.0 * weight / (nx * nx),
-               2.0 * weight / (ny * ny), gscale.data_ptr() if gscale is not None else None, dy.data_ptr(),
-               int(accumulate), _stream(dev))
+    _launch(dev, ('tv_bwd', y.numel()), 'ast_tv_bwd', y.data_ptr(), c, h, w, sums2.data_ptr(), 2.0 * weight / (nx * nx),
+            2.0 * weight / (ny * ny), gscale.data_ptr() if gscale is not None else None, dy.data_ptr(),
+            int(accumulate))
 
 
 class TotalVariationFn(torch.autograd.Function):
@@ -305,13 +344,11 @@ def bicubic_down_raw(x: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
     x = x.contiguous()
     c, h, w = _planes(x)
     y = torch.empty(x.shape[:-2] + (out_h, out_w), dtype=torch.float32, device=x.device)
-    dev = x.device
-    with _on(dev):
-        if h == 2 * out_h and w == 2 * out_w:
-            L.call('ast_bicubic_down2x', x.data_ptr(), c, h, w, y.data_ptr(), _stream(dev))
-        else:
-            L.call('ast_bicubic_resize', x.data_ptr(), c, h, w, y.data_ptr(), out_h, out_w, L.AST_LAYOUT_CHW,
-                   L.AST_COORD_TORCH, _stream(dev))
+    if h == 2 * out_h and w == 2 * out_w:
+        _launch(x.device, ('down2x', c, h, w), 'ast_bicubic_down2x', x.data_ptr(), c, h, w, y.data_ptr())
+    else:
+        _launch(x.device, ('resize', c, h, w, out_h, out_w), 'ast_bicubic_resize', x.data_ptr(), c, h, w, y.data_ptr(),
+                out_h, out_w, L.AST_LAYOUT_CHW, L.AST_COORD_TORCH)
     return y
 
 
@@ -323,14 +360,12 @@ def bicubic_down_adj_raw(gy: torch.Tensor, in_h: int, in_w: int, gx: Optional[to
     if gx is None:
         gx = torch.empty(gy.shape[:-2] + (in_h, in_w), dtype=torch.float32, device=gy.device)
         accumulate = False
-    dev = gy.device
-    with _on(dev):
-        if in_h == 2 * oh and in_w == 2 * ow:
-            L.call('ast_bicubic_down2x_adj', gy.data_ptr(), c, in_h, in_w, gx.data_ptr(), int(accumulate),
-                   _stream(dev))
-        else:
-            L.call('ast_bicubic_resize_adj', gy.data_ptr(), c, in_h, in_w, oh, ow, gx.data_ptr(), int(accumulate),
-                   L.AST_COORD_TORCH, _stream(dev))
+    if in_h == 2 * oh and in_w == 2 * ow:
+        _launch(gy.device, ('down2x_adj', c, in_h, in_w), 'ast_bicubic_down2x_adj', gy.data_ptr(), c, in_h, in_w,
+                gx.data_ptr(), int(accumulate))
+    else:
+        _launch(gy.device, ('resize_adj', c, in_h, in_w, oh, ow), 'ast_bicubic_resize_adj', gy.data_ptr(), c, in_h, in_w,
+                oh, ow, gx.data_ptr(), int(accumulate), L.AST_COORD_TORCH)
     return gx
 
 
@@ -365,8 +400,8 @@ def bicubic_resize(x: torch.Tensor, out_h: int, out_w: int, layout: str = 'chw',
         c, h, w = _planes(x)
         y = torch.empty(x.shape[:-2] + (out_h, out_w), dtype=torch.float32, device=dev)
         lay = L.AST_LAYOUT_CHW
-    with _on(dev):
-        L.call('ast_bicubic_resize', x.data_ptr(), c, h, w, y.data_ptr(), out_h, out_w, lay, cm, _stream(dev))
+    _launch(dev, ('resize', c, h, w, out_h, out_w), 'ast_bicubic_resize', x.data_ptr(), c, h, w, y.data_ptr(), out_h,
+            out_w, lay, cm)
     return y
 
 
@@ -423,9 +458,8 @@ class LevelLossFn(torch.autograd.Function):
         mse_fwd(content_feat, target_content, 1.0 / content_feat.numel(), vals[n_style], wss.for_reduce('content', dev))
         sums2 = torch.empty(2, dtype=torch.float32, device=dev)
         tv_fwd(img, sums2, vals[n_style + 1], wss.for_reduce('tv', dev))
-        with _on(dev):
-            L.call('ast_level_combine', vals.data_ptr(), n_style, vals[n_style].data_ptr(),
-                   vals[n_style + 1].data_ptr(), cw, sw, tvw, out4.data_ptr(), _stream(dev))
+        _launch(dev, ('combine',), 'ast_level_combine', vals.data_ptr(), n_style, vals[n_style].data_ptr(),
+                vals[n_style + 1].data_ptr(), cw, sw, tvw, out4.data_ptr())
         ctx.save_for_backward(img, content_feat, target_content, sums2, *style_feats, *ds)
         ctx.n_style = n_style
         ctx.weights = (cw, sw, tvw)
@@ -497,8 +531,7 @@ def noise_init(content_hwc: Optional[torch.Tensor], H: int, W: int, levels: Sequ
     if content_hwc is not None:
         _require_cuda(content_hwc)
         content_hwc = content_hwc.contiguous()
-    with _on(device):
-        L.call('ast_noise_init', content_hwc.data_ptr() if content_hwc is not None else None, H, W,
-               C.cast(arr, C.POINTER(L.NoiseLevel)), len(levels), float(noise_factor), m, int(use_gradient_map),
-               float(blur_w0), float(blur_w1), out.data_ptr(), _stream(device))
+    _launch(device, ('noise_init', H, W), 'ast_noise_init', content_hwc.data_ptr() if content_hwc is not None else None,
+            H, W, C.cast(arr, C.POINTER(L.NoiseLevel)), len(levels), float(noise_factor), m, int(use_gradient_map),
+            float(blur_w0), float(blur_w1), out.data_ptr())
     return out

@@ -1,20 +1,247 @@
-"""Row-band sharding of a pyramid level across the GPUs of one box.  Filled in below; with a
-single process (no torch.distributed group) every hook is a no-op and the path is exactly the 1-GPU one."""
+"""Row-band sharding of the pyramid levels across the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Every rank holds the full optimizing
+image and an identical optimizer.  Per level and closure each rank
+  1. runs VGG19 (torch/cuDNN) on its band of rows plus an 80-row halo on interior sides (the receptive field
+     of relu5_1 is 156 px, so everything inside the band is exact; band edges are multiples of 16 so the four
+     2x2 max-pools never straddle ranks),
+  2. forms the RAW partial Grams F_r F_r^T of its band (the Gram's K dimension is the spatial index, so the
+     full Gram is the plain sum over ranks) and the partial content SSE, straight from the band rows of the
+     NCHW feature maps (pitched TMA loads, no copy),
+  3. joins ONE all-reduce(sum) of the packed buffer [G1 | G2 | G3 | G4 | G5 | content_sse] (~2.4 MB),
+  4. finalizes identically on every rank: 1/(C*HW), minus target, MSE, weighted total,
+and, backward, computes dF_r = s (G - A) F_r for its band only.  The image gradients of all ranks are
+all-reduced once per closure so the replicated optimizers stay bit-identical.  Total variation is evaluated
+on the whole (small) level image by every rank; only rank 0 contributes its gradient.
+
+The reference has no counterpart (a commented-out two-GPU round-robin, neural_style_transfer.py:238-243).
+"""
 from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
 
+HALO = 80            # rows; >= 78 = receptive-field radius of relu5_1, multiple of 16
+ALIGN = 16           # VGG19 down-samples by 16 up to relu5_1
+LAYER_STRIDE = {0: 1, 1: 2, 2: 4, 3: 8, 4: 8, 5: 16}     # feature index -> spatial stride (neural_nets.py:26-29)
+
+
+class BandPlan:
+    """Pure host logic: which image rows a rank owns and feeds to the network at one level."""
+
+    def __init__(self, height: int, rank: int, world: int, halo: int = HALO):
+        if not self.shardable(height, world):
+            raise ValueError(f'height {height} cannot be cut into {world} bands of a multiple of {ALIGN} rows')
+        band = height // world
+        self.height, self.rank, self.world = height, rank, world
+        self.r0, self.r1 = rank * band, (rank + 1) * band          # owned rows
+        self.lo, self.hi = max(0, self.r0 - halo), min(height, self.r1 + halo)   # rows fed to VGG
+
+    @staticmethod
+    def shardable(height: int, world: int) -> bool:
+        return world >= 1 and height % world == 0 and (height // world) % ALIGN == 0 and height // world >= 2 * ALIGN
+
+    def feat_rows(self, stride: int):
+        """(first owned row, one-past-last owned row, rows present) in a feature map of the given stride."""
+        return (self.r0 - self.lo) // stride, (self.r1 - self.lo) // stride, (self.hi - self.lo) // stride
+
+    def global_feat_rows(self, stride: int):
+        return self.r0 // stride, self.r1 // stride
+
+
+def pack_layout(channels: Sequence[int]):
+    """Offsets of the raw Grams in the all-reduced buffer; the content SSE sits in the last slot."""
+    offs, o = [], 0
+    for c in channels:
+        offs.append(o)
+        o += c * c
+    return offs, o, o + 1     # gram offsets, index of the content slot, total floats
+
+
+class TorchDistGroup:
+    """The collective used in production: torch.distributed (NCCL) on the current stream."""
+
+    def __init__(self):
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def all_reduce_sum(self, t: torch.Tensor) -> None:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+_GROUP = None     # set by init_sharding(); None -> single-process path
+
 
 def world():
-    if dist.is_available() and dist.is_initialized():
-        return dist.get_rank(), dist.get_world_size()
+    if _GROUP is not None:
+        return _GROUP.rank, _GROUP.world
     return 0, 1
 
 
-def maybe_shard(loss_builders, optimizing_img, neural_net, content_idx, style_idx, weights):
-    return None
+def init_sharding(group=None) -> None:
+    """Enable row-band sharding for subsequent NeuralStyleTransfer.process calls in this process.
+    group: object with rank, world and all_reduce_sum(tensor) (default: the initialized torch.distributed group)."""
+    global _GROUP
+    if group is None:
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError('init_sharding() needs an initialized torch.distributed process group')
+        group = TorchDistGroup()
+    _GROUP = group
 
 
-def sync_image_grad(optimizing_img):
-    return None
+def disable_sharding() -> None:
+    global _GROUP
+    _GROUP = None
+
+
+class ShardedLevel:
+    """Replaces LossBuilder.build for one level when sharding is on (same return contract)."""
+
+    def __init__(self, group, neural_net, content_idx: int, style_idx: List[int], target_content: torch.Tensor,
+                 target_grams: List[torch.Tensor], weights, height: int, width: int, precision: int):
+        from . import ops
+        self.ops = ops
+        self.group = group
+        self.net = neural_net
+        self.cidx, self.sidx = content_idx, list(style_idx)
+        self.weights = tuple(float(w) for w in weights)
+        self.H, self.W = height, width
+        self.plan = BandPlan(height, group.rank, group.world)
+        self.precision = precision
+        self.target_grams = target_grams
+        cs = LAYER_STRIDE[content_idx]
+        ga, gb = self.plan.global_feat_rows(cs)
+        self.target_content_band = target_content[:, ga:gb, :].contiguous()
+        self.content_numel_global = target_content.numel()
+        self.channels = [g.shape[-1] for g in target_grams]
+        self.offs, self.content_slot, self.n_packed = pack_layout(self.channels)
+        self.wss = ops.LevelWorkspaces()
+        self.fin_ws = [None] * len(self.sidx)
+
+    def build(self, level_img: torch.Tensor):
+        x = level_img[:, :, self.plan.lo:self.plan.hi, :]
+        feats = self.net(x)
+        return ShardLevelLossFn.apply(self, level_img, feats[self.cidx], *[feats[k] for k in self.sidx])
+
+
+class ShardLevelLossFn(torch.autograd.Function):
+    """inputs: full level image (TV), band content map, band style maps.  outputs as LevelLossFn."""
+
+    @staticmethod
+    def forward(ctx, sh: ShardedLevel, level_img, content_feat, *style_feats):
+        ops = sh.ops
+        dev = ops._require_cuda(level_img, content_feat, *style_feats)
+        n_style = len(style_feats)
+        plan = sh.plan
+        cw, sw, tvw = sh.weights
+        level_img = level_img.contiguous()
+        style_feats = [f.contiguous() for f in style_feats]
+        packed = torch.zeros(sh.n_packed, dtype=torch.float32, device=dev)
+        geo = []
+        for k, f in enumerate(style_feats):
+            ch, hb, w = f.shape[-3], f.shape[-2], f.shape[-1]
+            a, b, rows = plan.feat_rows(LAYER_STRIDE[sh.sidx[k]])
+            assert rows == hb and ch == sh.channels[k], (rows, hb, ch)
+            hw_band, ld, off = (b - a) * w, hb * w, a * w
+            raw = packed[sh.offs[k]:sh.offs[k] + ch * ch]
+            ops.gram_mse_fwd(f, ch, hw_band, 1.0, None, raw, None, sh.wss.for_gram(k, ch, hw_band, dev), sh.precision,
+                             ld=ld, offset=off)
+            geo.append((ch, hw_band, ld, off, (sh.H // LAYER_STRIDE[sh.sidx[k]]) * (sh.W // LAYER_STRIDE[sh.sidx[k]])))
+        ca, cb, _ = plan.feat_rows(LAYER_STRIDE[sh.cidx])
+        x_band = content_feat[0, :, ca:cb, :].contiguous()
+        ops.mse_fwd(x_band, sh.target_content_band, 1.0, packed[sh.content_slot], sh.wss.for_reduce('content', dev))
+        sh.group.all_reduce_sum(packed)                      # the one exchange step of the level
+        vals = torch.empty(n_style + 2, dtype=torch.float32, device=dev)
+        out4 = torch.empty(4, dtype=torch.float32, device=dev)
+        ds = []
+        for k in range(n_style):
+            ch, hw_global = geo[k][0], geo[k][4]
+            d = torch.empty((ch, ch), dtype=torch.float32, device=dev)
+            if sh.fin_ws[k] is None or sh.fin_ws[k].buf.device != dev:
+                sh.fin_ws[k] = ops.reduce_workspace(dev)
+            ops.gram_finalize(packed[sh.offs[k]:sh.offs[k] + ch * ch], ch, 1.0 / (ch * hw_global), sh.target_grams[k],
+                              d, vals[k], sh.fin_ws[k])
+            ds.append(d)
+        torch.mul(packed[sh.content_slot], 1.0 / sh.content_numel_global, out=vals[n_style])
+        sums2 = torch.empty(2, dtype=torch.float32, device=dev)
+        ops.tv_fwd(level_img, sums2, vals[n_style + 1], sh.wss.for_reduce('tv', dev))
+        ops._launch(dev, ('combine',), 'ast_level_combine', vals.data_ptr(), n_style, vals[n_style].data_ptr(),
+                    vals[n_style + 1].data_ptr(), cw, sw, tvw, out4.data_ptr())
+        ctx.save_for_backward(level_img, x_band, sums2, *style_feats, *ds)
+        ctx.sh, ctx.geo, ctx.n_style = sh, geo, n_style
+        ctx.content_shape, ctx.content_rows = content_feat.shape, (ca, cb)
+        total, content, style, tv = out4[0], out4[1], out4[2], out4[3]
+        ctx.mark_non_differentiable(content, style, tv)
+        return total, content, style, tv
+
+    @staticmethod
+    def backward(ctx, g_total, g_content, g_style, g_tv):
+        sh = ctx.sh
+        ops = sh.ops
+        saved = ctx.saved_tensors
+        level_img, x_band, sums2 = saved[:3]
+        n = ctx.n_style
+        style_feats, ds = saved[3:3 + n], saved[3 + n:3 + 2 * n]
+        cw, sw, tvw = sh.weights
+        dev = level_img.device
+        g = ops._gscale(g_total, dev)
+        need = ctx.needs_input_grad          # (sh, level_img, content_feat, *style_feats)
+        d_img = d_content = None
+        if need[1] and sh.group.rank == 0:   # TV is replicated: count its gradient once
+            d_img = torch.empty_like(level_img)
+            ops.tv_bwd(level_img, sums2, tvw, g, d_img, False)
+        if need[2]:
+            ca, cb = ctx.content_rows
+            d_content = torch.zeros(ctx.content_shape, dtype=torch.float32, device=dev)
+            band = torch.empty_like(x_band)
+            ops.mse_bwd(x_band, sh.target_content_band, cw * 2.0 / sh.content_numel_global, g, band, False)
+            d_content[0, :, ca:cb, :] = band
+        d_style = []
+        for k in range(n):
+            if not need[3 + k]:
+                d_style.append(None)
+                continue
+            f = style_feats[k]
+            ch, hw_band, ld, off, hw_global = ctx.geo[k]
+            w = f.shape[-1]
+            a, b = off // w, (off + hw_band) // w
+            df = torch.empty_like(f)
+            if a > 0:
+                df[..., :a, :].zero_()
+            if b < f.shape[-2]:
+                df[..., b:, :].zero_()
+            ops.gram_bwd(ds[k], f, ch, hw_band, (sw / n) * 4.0 / (float(ch) * ch * ch * hw_global), g, df, False,
+                         sh.precision, ld=ld, offset=off)
+            d_style.append(df)
+        return (None, d_img, d_content, *d_style)
+
+
+def maybe_shard(loss_builders, optimizing_img, neural_net, content_idx, style_idx, weights) -> int:
+    """Hook called by NeuralStyleTransfer.process after the per-level LossBuilders exist.  Returns the number of
+    levels that were sharded (0 on the single-process path)."""
+    if _GROUP is None or _GROUP.world == 1 and os.environ.get('AST_SHARD_SINGLE', '0') != '1':
+        return 0
+    from . import ops, neural_style_transfer as nst
+    h, w = optimizing_img.shape[-2], optimizing_img.shape[-1]
+    n = 0
+    for i, lb in enumerate(loss_builders):
+        lh, lw = h >> i, w >> i
+        if BandPlan.shardable(lh, _GROUP.world) and lw % ALIGN == 0 and (h % (1 << i) == 0):
+            grams = [g[0].detach().contiguous() for g in lb.target_style_representation]
+            lb.shard = ShardedLevel(_GROUP, neural_net, content_idx, style_idx, lb.target_content_representation,
+                                    grams, weights, lh, lw, ops._prec(nst.PRECISION))
+            n += 1
+        else:
+            lb.replicated_rank0_only = _GROUP.rank != 0
+    return n
+
+
+def sync_image_grad(optimizing_img) -> None:
+    """All-reduce(sum) of the image gradient so that every rank steps an identical optimizer."""
+    if _GROUP is None or _GROUP.world == 1:
+        return
+    if optimizing_img.grad is None:          # every rank must join the collective
+        optimizing_img.grad = torch.zeros_like(optimizing_img)
+    _GROUP.all_reduce_sum(optimizing_img.grad)

@@ -64,9 +64,11 @@ int         ast_device_check(void);
  * Plain Gram: A = NULL, loss = NULL.  Row-band sharding: scale = 1, A = NULL gives the raw
  * partial sum to all-reduce, then ast_gram_finalize applies scale / A / MSE on every rank.
  * ws must hold ast_gram_workspace_bytes(C, HW) bytes.
+ * ld = row pitch of F in elements (ld >= HW; pass HW for a dense (C, HW) map).  A row band
+ * [a, b) of an NCHW map (C, h, w) is F + a*w with HW = (b-a)*w and ld = h*w: no copy needed.
  */
 size_t ast_gram_workspace_bytes(int C, int64_t HW);
-int ast_gram_mse_fwd(const float* F, int C, int64_t HW, float scale, const float* A,
+int ast_gram_mse_fwd(const float* F, int C, int64_t HW, int64_t ld, float scale, const float* A,
                      float* out, float* loss, void* ws, size_t ws_bytes, int precision,
                      void* stream);
 int ast_gram_finalize(const float* G_raw, int C, float scale, const float* A, float* out,
@@ -74,10 +76,10 @@ int ast_gram_finalize(const float* G_raw, int C, float scale, const float* A, fl
 
 /* Backward of the style term (autograd of bmm + MSELoss in the reference, 2 bmm per layer):
  *   dF[C,HW] (+)= scale * D D-symmetric [C,C] * F[C,HW]
- * with scale = 4 / (C^2 * C*HW) on the host and the upstream gradient read on the device:
+ * (F and dF share the row pitch ld) with scale = 4 / (C^2 * C*HW) on the host and the upstream gradient read on the device:
  * every *_bwd entry point multiplies its host scale by *gscale when gscale != NULL (a device
  * float, e.g. autograd's grad_output), so no host synchronisation is needed. */
-int ast_gram_bwd(const float* D, const float* F, int C, int64_t HW, float scale,
+int ast_gram_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, float scale,
                  const float* gscale, float* dF, int accumulate, int precision, void* stream);
 
 /* ---- Content MSE (neural_style_transfer.py:95) ---------------------------------------------

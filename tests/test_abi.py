@@ -50,9 +50,9 @@ def test_argument_validation_without_gpu(lib):
     p = ctypes.addressof(buf)
     rc = lib.ast_bicubic_down2x(p, 3, 7, 8, p, None)
     assert rc == -3 and b'even' in lib.ast_last_error()
-    rc = lib.ast_gram_mse_fwd(p, 48, 64, 1.0, None, p, None, p, 1 << 30, 0, None)
+    rc = lib.ast_gram_mse_fwd(p, 48, 64, 64, 1.0, None, p, None, p, 1 << 30, 0, None)
     assert rc == -3 and b'multiple of 64' in lib.ast_last_error()
-    rc = lib.ast_gram_mse_fwd(p, 64, 64, 1.0, None, p, None, p, 16, 0, None)
+    rc = lib.ast_gram_mse_fwd(p, 64, 64, 64, 1.0, None, p, None, p, 16, 0, None)
     assert rc == -4
     with pytest.raises(RuntimeError, match='ast_mse_bwd failed'):
         _lib.call('ast_mse_bwd', None, None, 1, 1.0, None, None, 0, None)

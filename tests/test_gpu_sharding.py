@@ -1,0 +1,111 @@
+"""GPU: the row-band sharded level (artstyletransfer_b200/parallel.py) on ONE device — R ranks emulated as R host
+threads sharing the default stream, with an in-process collective — vs the unsharded level.  Checks the pitched
+partial-Gram loads, the packed all-reduce layout, ast_gram_finalize, halo cropping and the gradient sum."""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gatys_oracle as O
+
+pytestmark = pytest.mark.gpu
+WEIGHTS = (1e3, 4e5, 1e2)
+
+
+def dev():
+    return torch.device('cuda', 0)
+
+
+class ThreadGroup:
+    """all_reduce_sum across `world` threads of this process (fixed rank order -> deterministic)."""
+
+    def __init__(self, rank, world, shared):
+        self.rank, self.world, self.shared = rank, world, shared
+
+    def all_reduce_sum(self, t):
+        sh = self.shared
+        sh['bufs'][self.rank] = t
+        sh['barrier'].wait()
+        total = sh['bufs'][0].clone()
+        for r in range(1, self.world):
+            total = total + sh['bufs'][r]
+        sh['barrier'].wait()
+        t.copy_(total)
+        sh['barrier'].wait()
+
+
+@pytest.fixture(autouse=True)
+def exact_convs():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic = old
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32'])
+@pytest.mark.parametrize('world', [2, 4])
+def test_sharded_level_matches_unsharded(seeded_vgg, world, precision):
+    from artstyletransfer_b200 import math_utils, neural_style_transfer as nst, ops, parallel
+    H, W = 512, 64
+    content, style = O.synthetic_images(H, W, seed=5)
+    init = np.clip(content * 0.5 + np.random.default_rng(6).uniform(0, 1, size=content.shape) * 0.5, 0, 1).astype(np.float32)
+    nst.PRECISION = precision
+    try:
+        net, cidx, sidx = math_utils.prepare_model('vgg19', dev())
+        lb = nst.LossBuilder(cidx, sidx, nst.prepare_img(content, dev()), nst.prepare_img(style, dev()), net, *WEIGHTS)
+        img = nst.prepare_img(init, dev()).requires_grad_(True)
+        total, c, s, tv = lb.build(img)
+        total.backward()
+        ref = [v.item() for v in (total, c, s, tv)]
+        ref_grad = img.grad.clone()
+
+        shared = {'bufs': [None] * world, 'barrier': threading.Barrier(world)}
+        grams = [g[0].detach().contiguous() for g in lb.target_style_representation]
+        results = [None] * world
+        errors = []
+
+        def run(rank):
+            try:
+                torch.cuda.set_device(dev())
+                grp = ThreadGroup(rank, world, shared)
+                sh = parallel.ShardedLevel(grp, net, cidx, sidx, lb.target_content_representation, grams, WEIGHTS, H, W,
+                                           ops._prec(precision))
+                x = nst.prepare_img(init, dev()).requires_grad_(True)
+                t, cc, ss, vv = sh.build(x)
+                t.backward()
+                results[rank] = ([v.item() for v in (t, cc, ss, vv)], x.grad.clone())
+            except Exception as e:   # pragma: no cover
+                errors.append(e)
+                shared['barrier'].abort()
+
+        threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        assert not errors, errors
+    finally:
+        nst.PRECISION = None
+    tol = 2e-5 if precision == 'fp32' else 2e-4
+    for r in range(world):
+        np.testing.assert_allclose(results[r][0], ref, rtol=tol)
+        assert results[r][0] == results[0][0]                 # every rank sees bit-identical losses
+    gsum = sum(results[r][1] for r in range(world))
+    gerr = float(torch.linalg.norm(gsum - ref_grad) / torch.linalg.norm(ref_grad))
+    assert gerr < (1e-4 if precision == 'fp32' else 2e-3)
+
+
+def test_band_plan_and_pack_layout():
+    from artstyletransfer_b200.parallel import BandPlan, pack_layout
+    rows = []
+    for r in range(8):
+        p = BandPlan(2048, r, 8)
+        assert (p.r1 - p.r0) == 256 and p.lo % 16 == 0 and p.hi % 16 == 0
+        assert p.r0 - p.lo in (0, 80) and p.hi - p.r1 in (0, 80)
+        a, b, n = p.feat_rows(16)
+        assert b - a == 16 and n == (p.hi - p.lo) // 16
+        rows += list(range(p.r0, p.r1))
+    assert rows == list(range(2048))
+    offs, slot, n = pack_layout([64, 128, 256, 512, 512])
+    assert offs == [0, 4096, 20480, 86016, 348160] and slot == 610304 and n == 610305
+    assert not BandPlan.shardable(383, 2) and BandPlan.shardable(256, 8) and not BandPlan.shardable(256, 16)
