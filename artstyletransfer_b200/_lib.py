@@ -37,6 +37,7 @@ SIGNATURES = {
     'ast_last_error': (C.c_char_p, []),
     'ast_device_check': (_i, []),
     'ast_gram_workspace_bytes': (_sz, [_i, _i64]),
+    'ast_gram_tf32_supported': (_i, [_p, _i, _i64, _i64]),
     'ast_gram_mse_fwd': (_i, [_p, _i, _i64, _i64, _f, _p, _p, _p, _p, _sz, _i, _p]),
     'ast_gram_finalize': (_i, [_p, _i, _f, _p, _p, _p, _p, _sz, _p]),
     'ast_gram_bwd': (_i, [_p, _p, _i, _i64, _i64, _f, _p, _p, _i, _i, _p]),

@@ -280,6 +280,10 @@ extern "C" size_t ast_gram_workspace_bytes(int C, int64_t HW) {
   return kGramWsHeaderBytes + parts * sizeof(float);
 }
 
+extern "C" int ast_gram_tf32_supported(const float* F, int C, int64_t HW, int64_t ld) {
+  return (gram_tc_supported(C, HW, F) && ld >= HW && (ld % 4 == 0)) ? 1 : 0;
+}
+
 extern "C" int ast_gram_mse_fwd(const float* F, int C, int64_t HW, int64_t ld, float scale, const float* A,
                                 float* out, float* loss, void* ws, size_t ws_bytes, int precision, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;

@@ -402,4 +402,10 @@ def unprepare_img(img: Tensor):
     t = img.detach()
     mean = torch.tensor(IMAGENET_MEAN_255, dtype=torch.float32, device=t.device).view(1, 3, 1, 1)
     hwc = ((t + mean) / 255).permute([0, 2, 3, 1]).squeeze(0).contiguous()
-    return hwc.to("cpu").numpy()
+    if not hwc.is_cuda:
+        return hwc.numpy()
+    # fresh page-locked block from torch's caching host allocator (recycled once the caller drops the array)
+    host = torch.empty(hwc.shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(hwc, non_blocking=True)
+    torch.cuda.current_stream(hwc.device).synchronize()
+    return host.numpy()

@@ -151,10 +151,19 @@ def _thread_ws(kind: str, nbytes: int, device: torch.device) -> Workspace:
 # ------------------------------------------------------------------------------------------------------
 # raw launches
 # ------------------------------------------------------------------------------------------------------
+def effective_precision(precision: int, ptr: int, C: int, HW: int, ld: int) -> int:
+    """TF32 (tcgen05/TMA) when the operand is addressable by TMA, else the exact fp32 CUDA kernels — still this
+    library's sm_100a code, never a CPU or torch fallback.  Only toy shapes (HW % 4 != 0) take the second branch."""
+    if precision == L.AST_PREC_TF32 and not L.load().ast_gram_tf32_supported(ptr, C, HW, ld):
+        return L.AST_PREC_FP32
+    return precision
+
+
 def gram_mse_fwd(feat: torch.Tensor, C: int, HW: int, scale: float, target: Optional[torch.Tensor],
                  out: torch.Tensor, loss: Optional[torch.Tensor], ws: Workspace, precision: int,
                  ld: Optional[int] = None, offset: int = 0) -> None:
     """feat: base tensor; the (C, HW) operand starts `offset` elements in and has row pitch `ld` (default HW)."""
+    precision = effective_precision(precision, feat.data_ptr() + 4 * offset, C, HW, HW if ld is None else ld)
     _launch(feat.device, ('gram_fwd', C, HW, precision), 'ast_gram_mse_fwd', feat.data_ptr() + 4 * offset, C, HW,
             HW if ld is None else ld, scale,
             target.data_ptr() if target is not None else None, out.data_ptr(),
@@ -170,6 +179,9 @@ def gram_finalize(g_raw: torch.Tensor, C: int, scale: float, target: Optional[to
 
 def gram_bwd(D: torch.Tensor, feat: torch.Tensor, C: int, HW: int, scale: float, gscale: Optional[torch.Tensor],
              dF: torch.Tensor, accumulate: bool, precision: int, ld: Optional[int] = None, offset: int = 0) -> None:
+    precision = effective_precision(precision, feat.data_ptr() + 4 * offset, C, HW, HW if ld is None else ld)
+    if (dF.data_ptr() + 4 * offset) % 16 or D.data_ptr() % 16:
+        precision = L.AST_PREC_FP32
     _launch(feat.device, ('gram_bwd', C, HW, precision), 'ast_gram_bwd', D.data_ptr(), feat.data_ptr() + 4 * offset, C,
             HW, HW if ld is None else ld, scale, gscale.data_ptr() if gscale is not None else None,
             dF.data_ptr() + 4 * offset, int(accumulate), precision)

@@ -68,6 +68,9 @@ int         ast_device_check(void);
  * [a, b) of an NCHW map (C, h, w) is F + a*w with HW = (b-a)*w and ld = h*w: no copy needed.
  */
 size_t ast_gram_workspace_bytes(int C, int64_t HW);
+/* 1 when the tcgen05/TMA path (AST_PREC_TF32) can address this operand: C in {64,128,256,512}, HW and ld
+ * multiples of 4 elements (TMA strides are multiples of 16 bytes), F 16-byte aligned; else 0 (use AST_PREC_FP32). */
+int ast_gram_tf32_supported(const float* F, int C, int64_t HW, int64_t ld);
 int ast_gram_mse_fwd(const float* F, int C, int64_t HW, int64_t ld, float scale, const float* A,
                      float* out, float* loss, void* ws, size_t ws_bytes, int precision,
                      void* stream);

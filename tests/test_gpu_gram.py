@@ -64,10 +64,15 @@ def test_gram_matrix_golden(golden, precision):
 
 
 def test_gram_unsupported_shape_raises_for_tf32_but_fp32_works():
-    from artstyletransfer_b200 import math_utils
+    from artstyletransfer_b200 import math_utils, ops, _lib
     x = torch.rand(1, 64, 3, 5, device=dev())     # HW = 15: not a multiple of 4 -> no TMA path
-    with pytest.raises(RuntimeError, match='TF32 path'):
-        math_utils.gram_matrix(x, precision='tf32')
+    out = torch.empty(64, 64, device=dev())
+    assert _lib.load().ast_gram_tf32_supported(x.data_ptr(), 64, 15, 15) == 0
+    with pytest.raises(RuntimeError, match='TF32 path'):      # the C ABI refuses ...
+        _lib.call('ast_gram_mse_fwd', x.data_ptr(), 64, 15, 15, 1.0, None, out.data_ptr(), None,
+                  ops.gram_workspace(64, 15, dev()).ptr, 1 << 20, _lib.AST_PREC_TF32, None)
+    g = math_utils.gram_matrix(x, precision='tf32')            # ... the Python surface takes the exact CUDA kernel
+    assert rel(g.cpu().numpy(), O.gram_matrix(x.cpu().numpy())) < 2e-6
     g = math_utils.gram_matrix(x, precision='fp32')
     assert rel(g.cpu().numpy(), O.gram_matrix(x.cpu().numpy())) < 2e-6
     with pytest.raises(RuntimeError, match='multiple of 64'):
