@@ -43,7 +43,7 @@ L2_BYTES = 126e6
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--levels', type=int, default=LEVELS, help='pyramid levels (4 = the headline L=3 job)')
@@ -88,7 +88,10 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
@@ -96,7 +99,9 @@ class ClockSampler:
         time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        t0, t1 = getattr(self, 't0', 0.0), getattr(self, 't1', 1e30)
+        inside = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.25]
+        for ln in (inside or [ln for _, ln in self.lines[-3:]]):
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 9:
                 continue
@@ -232,21 +237,23 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        job.optimizer_step()
-    barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        job.optimizer_step()
+    barrier()
     ops.STATS.reset(enabled=True, timing=True)
     closures0 = job.step
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         job.optimizer_step()
     e1.record()
     barrier()
+    clocks.window(w0, time.perf_counter())
     ms = e0.elapsed_time(e1)
     closures = job.step - closures0
     launches = ops.STATS.launches
