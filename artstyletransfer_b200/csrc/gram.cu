@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(256) gram_fp32_bwd_kernel(const float* __restr
 
 // ------------------------------------------------------------------------------------------------------
 // finalize: out = scale * sum_p partial_p - A (mirrored for off-diagonal tiles); loss = mean(out^2).
-// Block = 64 float4 element groups x 4 partial lanes; lanes are combined in fixed order.
+// Block = (256/L) float4 element groups x L partial lanes (L = 4, 8 or 16, more lanes for small tiles so that the
+// grid still fills the machine); lanes are combined in fixed order.
 // ------------------------------------------------------------------------------------------------------
 struct FinalizeArgs {
   GramPlan plan;
@@ -161,32 +162,34 @@ struct FinalizeArgs {
   float* loss;         // nullable
   float scale;
   int symmetric_src;   // 1: partials hold only bi<=bj tiles (mirror them); 0: single full tile
+  int lanes;           // partial lanes per element group (4, 8, 16)
 };
 
 __global__ void __launch_bounds__(256) gram_finalize_kernel(const __grid_constant__ FinalizeArgs a, ReduceWs* ws) {
-  __shared__ float4 lanes[4][64];
+  __shared__ float4 lanes[256];
   __shared__ double red[32];
   const GramPlan& pl = a.plan;
   const int TR = pl.TR, C = pl.C;
-  const int blocks_per_tile = (TR * TR) / 256;
+  const int L = a.lanes, groups = 256 / L;
+  const int elems_per_block = groups * 4;
+  const int blocks_per_tile = (TR * TR) / elems_per_block;
   const int t = blockIdx.x / blocks_per_tile;
   const int eb = blockIdx.x - t * blocks_per_tile;
-  const int g = threadIdx.x & 63, lane = threadIdx.x >> 6;
-  const int e0 = eb * 256 + g * 4;  // first of 4 consecutive elements inside the tile
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const int e0 = eb * elems_per_block + g * 4;  // first of 4 consecutive elements inside the tile
   const float* base = a.partials + (size_t)pl.part_off[t] * TR * TR + e0;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int p = lane; p < pl.part_cnt[t]; p += 4) {
+  for (int p = lane; p < pl.part_cnt[t]; p += L) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * TR * TR));
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
-  lanes[lane][g] = s;
+  lanes[lane * groups + g] = s;
   __syncthreads();
   double sq = 0.0;
   if (lane == 0) {
-    float4 tot = lanes[0][g];
-#pragma unroll
-    for (int l = 1; l < 4; ++l) {
-      const float4 v = lanes[l][g];
+    float4 tot = lanes[g];
+    for (int l = 1; l < L; ++l) {
+      const float4 v = lanes[l * groups + g];
       tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
     }
     const int r = e0 / TR, c = e0 - r * TR;
@@ -229,7 +232,10 @@ static int launch_finalize(const GramPlan& plan, const float* partials, int symm
   fa.loss = loss;
   fa.scale = scale;
   fa.symmetric_src = symmetric_src;
-  const int blocks = plan.n_tiles * (plan.TR * plan.TR / 256);
+  const int elems = plan.n_tiles * plan.TR * plan.TR;
+  fa.lanes = (elems <= 4096) ? 16 : (elems <= 16384 ? 8 : 4);
+  if (plan.total_parts < 2 * fa.lanes) fa.lanes = 4;
+  const int blocks = elems / ((256 / fa.lanes) * 4);
   if (blocks > kReduceMaxBlocks) {
     set_error("gram finalize: %d blocks exceed the reduce workspace", blocks);
     return AST_ERR_UNSUPPORTED;

@@ -72,15 +72,23 @@ static int make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t 
 // ------------------------------------------------------------------------------------------------------
 // shared device pieces
 // ------------------------------------------------------------------------------------------------------
-// Round `bytes` of staged fp32 to nearest TF32 in place; 128 converter threads, 16 B per access.
+// Round `bytes` of staged fp32 to nearest TF32 in place; 128 converter threads, 16 B per access, explicit
+// shared-space LDS.128 / STS.128 (a generic pointer would compile to LD.E / ST.E and double the wavefronts).
+// tcgen05 drops the low 13 mantissa bits itself, so adding half a TF32 ulp (0x1000) to the bit pattern is the
+// whole rounding (round-half-away on the magnitude); Inf/NaN patterns are left untouched.
+__device__ __forceinline__ uint32_t tf32_half_ulp(uint32_t u) {
+  return ((u & 0x7f800000u) == 0x7f800000u) ? u : u + 0x1000u;
+}
 __device__ __forceinline__ void convert_tf32_inplace(uint8_t* base, int bytes, int ctid) {
-  float4* p = reinterpret_cast<float4*>(base);
+  const uint32_t s0 = smem_u32(base);
   const int n = bytes >> 4;
 #pragma unroll 4
   for (int i = ctid; i < n; i += 128) {
-    float4 v = p[i];
-    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
-    p[i] = v;
+    uint32_t a, b, c, d;
+    const uint32_t addr = s0 + 16u * (uint32_t)i;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+    a = tf32_half_ulp(a); b = tf32_half_ulp(b); c = tf32_half_ulp(c); d = tf32_half_ulp(d);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
   }
 }
 
