@@ -277,7 +277,7 @@ extern "C" size_t ast_gram_workspace_bytes(int C, int64_t HW) {
   if (C <= 0 || HW <= 0) return 0;
   size_t parts_fp32 = (C % SG_T == 0) ? (size_t)fp32_splits(C, HW) * C * C : 0;
   size_t parts_tc = 0;
-  if (gram_tc_supported(C, HW, nullptr)) {
+  if (C == 64 || C == 128 || C == 256 || C == 512) {   // either layout (the NHWC path has no HW % 4 limit)
     GramPlan plan;
     gram_tc_plan(C, HW, 148, &plan);   // workspace sized for a full B200; fewer SMs never need more
     parts_tc = (size_t)plan.total_parts * plan.TR * plan.TR;
@@ -309,7 +309,7 @@ extern "C" int ast_gram_mse_fwd(const float* F, int C, int64_t HW, int64_t ld, f
                 "aligned F (C=%d HW=%lld ld=%lld); use AST_PREC_FP32", C, (long long)HW, (long long)ld);
     const int sms = cached_num_sms();
     gram_tc_plan(C, HW, sms < 148 ? sms : 148, &plan);
-    int rc = gram_tc_fwd(F, C, HW, ld, partials, plan, sms, stream);
+    int rc = gram_tc_fwd(F, C, HW, ld, 0, partials, plan, sms, stream);
     if (rc != AST_OK) return rc;
     return launch_finalize(plan, partials, 1, scale, A, out, loss, ws, stream);
   }
@@ -325,6 +325,37 @@ extern "C" int ast_gram_mse_fwd(const float* F, int C, int64_t HW, int64_t ld, f
   plan.tile_bi[0] = plan.tile_bj[0] = 0;
   plan.part_off[0] = 0; plan.part_cnt[0] = splits; plan.total_parts = splits;
   return launch_finalize(plan, partials, 0, scale, A, out, loss, ws, stream);
+}
+
+extern "C" int ast_gram_mse_fwd_nhwc(const float* F, int C, int64_t HW, float scale, const float* A, float* out,
+                                     float* loss, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  AST_REQUIRE(F && out && ws, AST_ERR_INVALID, "ast_gram_mse_fwd_nhwc: null pointer");
+  AST_REQUIRE(HW > 0 && HW <= (int64_t)0x7fffff00, AST_ERR_INVALID, "ast_gram_mse_fwd_nhwc: bad HW=%lld", (long long)HW);
+  AST_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, AST_ERR_UNSUPPORTED,
+              "ast_gram_mse_fwd_nhwc: C must be 64, 128, 256 or 512 (got %d)", C);
+  AST_REQUIRE(is16(F) && is16(out) && (!A || is16(A)) && is16(ws), AST_ERR_INVALID,
+              "ast_gram_mse_fwd_nhwc: F/out/A/ws must be 16-byte aligned");
+  AST_REQUIRE(ws_bytes >= ast_gram_workspace_bytes(C, HW), AST_ERR_WORKSPACE, "ast_gram_mse_fwd_nhwc: workspace %zu < %zu",
+              ws_bytes, ast_gram_workspace_bytes(C, HW));
+  float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kGramWsHeaderBytes);
+  GramPlan plan;
+  const int sms = cached_num_sms();
+  gram_tc_plan(C, HW, sms < 148 ? sms : 148, &plan);
+  int rc = gram_tc_fwd(F, C, HW, C, 1, partials, plan, sms, stream);
+  if (rc != AST_OK) return rc;
+  return launch_finalize(plan, partials, 1, scale, A, out, loss, ws, stream);
+}
+
+extern "C" int ast_gram_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale,
+                                 float* dF, int accumulate, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  AST_REQUIRE(D && F && dF, AST_ERR_INVALID, "ast_gram_bwd_nhwc: null pointer");
+  AST_REQUIRE(HW > 0 && HW <= (int64_t)0x7fffff00, AST_ERR_INVALID, "ast_gram_bwd_nhwc: bad HW=%lld", (long long)HW);
+  AST_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, AST_ERR_UNSUPPORTED,
+              "ast_gram_bwd_nhwc: C must be 64, 128, 256 or 512 (got %d)", C);
+  AST_REQUIRE(is16(F) && is16(D) && is16(dF), AST_ERR_INVALID, "ast_gram_bwd_nhwc: D/F/dF must be 16-byte aligned");
+  return gram_tc_bwd_nhwc(D, F, C, HW, scale, gscale, dF, accumulate, cached_num_sms(), stream);
 }
 
 extern "C" int ast_gram_finalize(const float* G_raw, int C, float scale, const float* A, float* out, float* loss,

@@ -31,9 +31,14 @@ static_assert(sizeof(ReduceWs) <= kGramWsHeaderBytes, "reduce header too small")
 bool gram_tc_supported(int C, int64_t HW, const void* F);
 // Plans the split-K decomposition for `num_sms` SMs (no device access).
 void gram_tc_plan(int C, int64_t HW, int num_sms, GramPlan* plan);
-int gram_tc_fwd(const float* F, int C, int64_t HW, int64_t ld, float* partials, const GramPlan& plan, int num_sms,
-                cudaStream_t stream);
+// nhwc = 0: F is (C, HW) with row pitch ld (torch NCHW).  nhwc = 1: F is (HW, C) dense (torch channels_last).
+int gram_tc_fwd(const float* F, int C, int64_t HW, int64_t ld, int nhwc, float* partials, const GramPlan& plan,
+                int num_sms, cudaStream_t stream);
 int gram_tc_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, float scale, const float* gscale,
                 float* dF, int accumulate, int num_sms, cudaStream_t stream);
+
+// (HW, C) layout: dF[p, c] (+)= scale * sum_k F[p, k] D[c, k]
+int gram_tc_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale, float* dF,
+                     int accumulate, int num_sms, cudaStream_t stream);
 
 }  // namespace ast

@@ -17,6 +17,9 @@
 //
 // Pipeline per stage:  TMA (warp 0) --full--> converters (4 warps) --conv--> MMA (warp 1) --empty--> TMA
 // and                  MMA --acc_full--> epilogue warps (tcgen05.ld) [--acc_empty--> MMA in the backward].
+#include <cstdio>
+#include <cstdlib>
+
 #include "gram.cuh"
 #include "sm100_ptx.cuh"
 
@@ -69,6 +72,30 @@ static int make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t 
   return AST_OK;
 }
 
+// (HW, C) row-major fp32 operand viewed as (32 channels, HW positions, C/32 strips); box = 32 x 32 x box_strips
+// lands in shared memory as box_strips consecutive 4 KB strips of [32 positions][32 channels] in the
+// SWIZZLE_128B_BASE32B pattern tcgen05 needs for an MN-major 32-bit operand.  Positions >= HW read as zero.
+static int make_tmap_nhwc_strips(CUtensorMap* m, const float* base, int C, uint64_t HW, uint32_t box_strips) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return AST_ERR_CUDA;
+  }
+  cuuint64_t gdim[3] = {32, HW, (cuuint64_t)(C / 32)};
+  cuuint64_t gstride[2] = {(cuuint64_t)C * sizeof(float), 32 * sizeof(float)};
+  cuuint32_t box[3] = {32, 32, box_strips};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (nhwc strips) failed (CUresult %d) C=%d HW=%llu", (int)r, C,
+              (unsigned long long)HW);
+    return AST_ERR_CUDA;
+  }
+  return AST_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // shared device pieces
 // ------------------------------------------------------------------------------------------------------
@@ -82,8 +109,27 @@ __device__ __forceinline__ uint32_t tf32_half_ulp(uint32_t u) {
 __device__ __forceinline__ void convert_tf32_inplace(uint8_t* base, int bytes, int ctid) {
   const uint32_t s0 = smem_u32(base);
   const int n = bytes >> 4;
-#pragma unroll 4
-  for (int i = ctid; i < n; i += 128) {
+  // batches of 8 independent 16-byte accesses per thread (16 KB per batch for the 128 threads): the eight
+  // LDS.128 are in flight together, so a batch costs one shared-memory round trip instead of eight
+  int i = ctid;
+  for (; i + 7 * 128 < n; i += 8 * 128) {
+    uint32_t v[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t addr = s0 + 16u * (uint32_t)(i + j * 128);
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(v[j][0]), "=r"(v[j][1]), "=r"(v[j][2]), "=r"(v[j][3])
+                   : "r"(addr));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t addr = s0 + 16u * (uint32_t)(i + j * 128);
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(tf32_half_ulp(v[j][0])),
+                   "r"(tf32_half_ulp(v[j][1])), "r"(tf32_half_ulp(v[j][2])), "r"(tf32_half_ulp(v[j][3]))
+                   : "memory");
+    }
+  }
+  for (; i < n; i += 128) {
     uint32_t a, b, c, d;
     const uint32_t addr = s0 + 16u * (uint32_t)i;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
@@ -99,26 +145,40 @@ struct FwdParams {
   int tile_bi[kGramMaxTiles], tile_bj[kGramMaxTiles];
   int part_off[kGramMaxTiles];
   int units_total;                  // K units (stage fills) covering HW
+  int skip_rounding;                // tuning probe only (AST_GRAM_FWD_NOROUND=1): leave the operands truncated
   float* partials;
 };
 
-template <int C>
+// NU = K units per pipeline stage (one mbarrier round trip per stage), G = converter groups of 128 threads;
+// group g rounds stages g, g+G, ... so G stages are being rounded concurrently.
+template <int C, int NU, int G>
 struct FwdCfg {
-  static constexpr int kUnitChunks = (C == 64) ? 2 : 1;               // 32-wide K chunks per stage
   static constexpr int kBoxRows = (C == 64) ? 64 : (C == 128 ? 128 : 256);
-  static constexpr int kStageBytes = (C == 512) ? 65536 : (C == 256 ? 32768 : 16384);
-  static constexpr int kStages = (C == 512) ? 3 : (C == 256 ? 6 : 8);
+  // shared memory per K unit: C=64 two stacked 64x32 chunks, C=128 one 128x32 chunk, C=256 one 256x32 chunk,
+  // C=512 room for two 256x32 chunks (the diagonal tiles fill only the first)
+  static constexpr int kUnitBytes = (C == 512) ? 65536 : (C == 256 ? 32768 : 16384);
+  static constexpr int kStageBytes = NU * kUnitBytes;
+  static constexpr int kStagesFit = (208 * 1024) / kStageBytes;
+  static constexpr int kStagesCap = kStagesFit > 12 ? 12 : kStagesFit;
+  static constexpr int kStages = kStagesCap - (kStagesCap % G);
+  static constexpr int kThreads = 64 + 128 * G;
   static constexpr int kTmemCols = (C <= 128) ? 128 : 512;
   static constexpr int kTR = (C <= 256) ? C : 256;                     // partial tile edge
   static constexpr int kUmmaN = (C <= 128) ? 128 : 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + kBarBytes;
+  static_assert(kStages >= 2, "pipeline needs two stages");
+  // a converter group must always meet the same stage slots: with kStages % G != 0 a group can reach a slot whose
+  // previous fill (converted by ANOTHER group) has not landed yet and pass the parity wait spuriously
+  static_assert(kStages % G == 0 || G == 1, "kStages must be a multiple of the converter groups");
+  static_assert((3 * kStages + 1) * 8 + 8 <= kBarBytes, "barrier area too small");
 };
 
-// warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: converters then epilogue.
-template <int C>
-__global__ void __launch_bounds__(192, 1) gram_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                            const __grid_constant__ FwdParams P) {
-  using Cfg = FwdCfg<C>;
+// warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..2+4G: converters, then epilogue.
+template <int C, int NU, int G, bool NHWC>
+__global__ void __launch_bounds__(64 + 128 * G, 1) gram_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                    const __grid_constant__ FwdParams P) {
+  using Cfg = FwdCfg<C, NU, G>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -137,8 +197,9 @@ __global__ void __launch_bounds__(192, 1) gram_fwd_tc_kernel(const __grid_consta
   const int base_u = P.units_total / nsplit, rem_u = P.units_total % nsplit;
   const int u_begin = split * base_u + min(split, rem_u);
   const int n_units = base_u + (split < rem_u ? 1 : 0);
+  const int n_stages = (n_units + NU - 1) / NU;
   const bool offdiag = (C == 512) && (P.tile_bi[t] != P.tile_bj[t]);
-  const int stage_tx_bytes = (C == 512) ? (offdiag ? 65536 : 32768) : Cfg::kStageBytes;
+  const int unit_tx_bytes = (C == 512) ? (offdiag ? 65536 : 32768) : Cfg::kUnitBytes;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap);
@@ -162,44 +223,74 @@ __global__ void __launch_bounds__(192, 1) gram_fwd_tc_kernel(const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int i = 0; i < n_units; ++i) {
+      for (int i = 0; i < n_stages; ++i) {
         const int s = i % S;
         const uint32_t ph = (uint32_t)(i / S) & 1u;
+        const int nu = min(NU, n_units - i * NU);
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)stage_tx_bytes);
-        const uint32_t dst = smem_u32(smem + s * Cfg::kStageBytes);
-        const int u = u_begin + i;
-        if (C == 64) {
-          tma_load_2d(dst, &tmap, bar_full + 8 * s, (2 * u) * BK, 0);
-          tma_load_2d(dst + 64 * ROW_BYTES, &tmap, bar_full + 8 * s, (2 * u + 1) * BK, 0);
-        } else if (C <= 256) {
-          tma_load_2d(dst, &tmap, bar_full + 8 * s, u * BK, 0);
-        } else {
-          tma_load_2d(dst, &tmap, bar_full + 8 * s, u * BK, P.tile_bi[t] * 256);
-          if (offdiag) tma_load_2d(dst + 256 * ROW_BYTES, &tmap, bar_full + 8 * s, u * BK, P.tile_bj[t] * 256);
+        mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(nu * unit_tx_bytes));
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          if (j < nu) {
+            const uint32_t dst = smem_u32(smem + s * Cfg::kStageBytes + j * Cfg::kUnitBytes);
+            const int u = u_begin + i * NU + j;
+            if (NHWC) {
+              // (HW, C) operand: 4 KB strips of [32 positions][32 channels]; coordinates (channel in strip,
+              // position, strip)
+              if (C == 64) {
+                tma_load_3d(dst, &tmap, bar_full + 8 * s, 0, (2 * u) * BK, 0);
+                tma_load_3d(dst + 2 * 4096, &tmap, bar_full + 8 * s, 0, (2 * u + 1) * BK, 0);
+              } else if (C <= 256) {
+                tma_load_3d(dst, &tmap, bar_full + 8 * s, 0, u * BK, 0);
+              } else {
+                tma_load_3d(dst, &tmap, bar_full + 8 * s, 0, u * BK, P.tile_bi[t] * 8);
+                if (offdiag) tma_load_3d(dst + 8 * 4096, &tmap, bar_full + 8 * s, 0, u * BK, P.tile_bj[t] * 8);
+              }
+            } else if (C == 64) {
+              tma_load_2d(dst, &tmap, bar_full + 8 * s, (2 * u) * BK, 0);
+              tma_load_2d(dst + 64 * ROW_BYTES, &tmap, bar_full + 8 * s, (2 * u + 1) * BK, 0);
+            } else if (C <= 256) {
+              tma_load_2d(dst, &tmap, bar_full + 8 * s, u * BK, 0);
+            } else {
+              tma_load_2d(dst, &tmap, bar_full + 8 * s, u * BK, P.tile_bi[t] * 256);
+              if (offdiag) tma_load_2d(dst + 256 * ROW_BYTES, &tmap, bar_full + 8 * s, u * BK, P.tile_bj[t] * 256);
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc_tf32(128, Cfg::kUmmaN, 0, 0);
-      for (int i = 0; i < n_units; ++i) {
+      constexpr uint32_t idesc = umma_idesc_tf32(128, Cfg::kUmmaN, NHWC ? 1 : 0, NHWC ? 1 : 0);
+      for (int i = 0; i < n_stages; ++i) {
         const int s = i % S;
         const uint32_t ph = (uint32_t)(i / S) & 1u;
+        const int nu = min(NU, n_units - i * NU);
         mbar_wait(bar_conv + 8 * s, ph);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t b_base = offdiag ? a_base + 256 * ROW_BYTES : a_base;
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-          const uint64_t bd = umma_desc_sw128(b_base + k * 32, 16, 1024);
-          if (C <= 128) {
-            umma_tf32(tmem_base, umma_desc_sw128(a_base + k * 32, 16, 1024), bd, idesc, acc);
-          } else {
-            umma_tf32(tmem_base, umma_desc_sw128(a_base + k * 32, 16, 1024), bd, idesc, acc);
-            umma_tf32(tmem_base + 256, umma_desc_sw128(a_base + 128 * ROW_BYTES + k * 32, 16, 1024), bd, idesc, acc);
+        for (int j = 0; j < NU; ++j) {
+          if (j < nu) {
+            const uint32_t a_base = smem_u32(smem + s * Cfg::kStageBytes + j * Cfg::kUnitBytes);
+            const uint32_t b_base = offdiag ? a_base + 256 * ROW_BYTES : a_base;
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint32_t acc = (i > 0 || j > 0 || k > 0) ? 1u : 0u;
+              if (NHWC) {
+                // MN-major operands (SWIZZLE_128B_BASE32B): 8 positions (1024 B) per K step, channel strips 4096 B
+                // apart (LBO), 4-row swizzle atoms 512 B apart (SBO)
+                const uint64_t bd = umma_desc(b_base + k * 1024, 4096, 512, 1);
+                umma_tf32(tmem_base, umma_desc(a_base + k * 1024, 4096, 512, 1), bd, idesc, acc);
+                if (C > 128) umma_tf32(tmem_base + 256, umma_desc(a_base + 4 * 4096 + k * 1024, 4096, 512, 1), bd, idesc, acc);
+              } else {
+                const uint64_t bd = umma_desc_sw128(b_base + k * 32, 16, 1024);
+                umma_tf32(tmem_base, umma_desc_sw128(a_base + k * 32, 16, 1024), bd, idesc, acc);
+                if (C > 128)
+                  umma_tf32(tmem_base + 256, umma_desc_sw128(a_base + 128 * ROW_BYTES + k * 32, 16, 1024), bd, idesc,
+                            acc);
+              }
+            }
           }
         }
         umma_commit(bar_empty + 8 * s);
@@ -207,13 +298,21 @@ __global__ void __launch_bounds__(192, 1) gram_fwd_tc_kernel(const __grid_consta
       umma_commit(bar_acc);
     }
   } else {
-    // ===== converters (128 threads), then epilogue =====
-    const int ctid = threadIdx.x - 64;
-    for (int i = 0; i < n_units; ++i) {
+    // ===== converters (G groups of 128 threads), then epilogue =====
+    const int grp = (warp - 2) >> 2;
+    const int ctid = (threadIdx.x - 64) & 127;
+    for (int i = grp; i < n_stages; i += G) {
       const int s = i % S;
       const uint32_t ph = (uint32_t)(i / S) & 1u;
+      const int nu = min(NU, n_units - i * NU);
       mbar_wait(bar_full + 8 * s, ph);
-      convert_tf32_inplace(smem + s * Cfg::kStageBytes, stage_tx_bytes, ctid);
+      if (P.skip_rounding) {
+      } else if (unit_tx_bytes == Cfg::kUnitBytes) {
+        convert_tf32_inplace(smem + s * Cfg::kStageBytes, nu * Cfg::kUnitBytes, ctid);
+      } else {
+        for (int j = 0; j < nu; ++j)
+          convert_tf32_inplace(smem + s * Cfg::kStageBytes + j * Cfg::kUnitBytes, unit_tx_bytes, ctid);
+      }
       fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(bar_conv + 8 * s);
     }
@@ -223,39 +322,25 @@ __global__ void __launch_bounds__(192, 1) gram_fwd_tc_kernel(const __grid_consta
     const int row = sub * 32 + lane;     // accumulator lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(sub * 32) << 16);
     constexpr int TR = Cfg::kTR;
+    constexpr int kRowBlocks = (C <= 128) ? 1 : 2;
+    constexpr int kColGroups = (C == 64) ? 2 : (C == 128 ? 4 : 8);   // 32-column groups per accumulator row
     uint32_t v[32];
-    if (C == 64) {
-      // stacked units: rows 0..63 x cols 0..63 and rows 64..127 x cols 64..127 are two partial Grams
-      const int half = row >> 6;
-      float* dst = P.partials + ((size_t)(P.part_off[t] + 2 * split + half) * TR + (row & 63)) * TR;
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        tmem_ld_x32(lane_addr + half * 64 + g * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          reinterpret_cast<float4*>(dst + g * 32)[q] =
-              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                          __uint_as_float(v[4 * q + 3]));
-      }
-    } else {
-      constexpr int kRowBlocks = (C == 128) ? 1 : 2;
-      constexpr int kCols = (C == 128) ? 128 : 256;
-      float* tile = P.partials + (size_t)(P.part_off[t] + split) * TR * TR;
+    // C == 64, stacked units: rows 0..63 x cols 0..63 and rows 64..127 x cols 64..127 are two partial Grams
+    const int half = (C == 64) ? (row >> 6) : 0;
+    float* tile = (C == 64)
+                      ? P.partials + ((size_t)(P.part_off[t] + 2 * split + half) * TR + (row & 63)) * TR
+                      : P.partials + (size_t)(P.part_off[t] + split) * TR * TR + (size_t)row * TR;
 #pragma unroll 1
-      for (int rb = 0; rb < kRowBlocks; ++rb) {
-        float* dst = tile + (size_t)(rb * 128 + row) * TR;
-#pragma unroll 1
-        for (int g = 0; g < kCols / 32; ++g) {
-          tmem_ld_x32(lane_addr + rb * 256 + g * 32, v);
-          tmem_ld_wait();
+    for (int q = grp; q < kRowBlocks * kColGroups; q += G) {
+      const int rb = q / kColGroups, cg = q % kColGroups;
+      tmem_ld_x32(lane_addr + rb * 256 + half * 64 + cg * 32, v);
+      tmem_ld_wait();
+      float* dst = tile + (size_t)(rb * 128) * TR + cg * 32;
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            reinterpret_cast<float4*>(dst + g * 32)[q] =
-                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                            __uint_as_float(v[4 * q + 3]));
-        }
-      }
+      for (int e = 0; e < 8; ++e)
+        reinterpret_cast<float4*>(dst)[e] =
+            make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                        __uint_as_float(v[4 * e + 3]));
     }
   }
   tc_fence_before();
@@ -457,6 +542,215 @@ __global__ void __launch_bounds__(320, 1) gram_bwd_tc_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------------
+// backward, (HW, C) layout (torch channels_last):  dF[p, c] (+)= s * sum_k F[p, k] D[c, k]
+// ------------------------------------------------------------------------------------------------------
+// A = F tile [128 positions x 32 channels] K-major (channels are contiguous), B = D chunk [C x 32] K-major, the
+// accumulator lane is the position and the column the output channel.  The epilogue stages each 32 x 32 block in
+// shared memory (128B swizzle, conflict-free) and hands it to TMA: a tiled store, or a tiled reduce-add when the
+// result accumulates into an existing gradient (the add happens in L2; the SM never reads dF).
+struct BwdNhwcParams {
+  int64_t HW;
+  int n_tiles;       // ceil(HW / 128)
+  float scale;
+  const float* gscale;
+  int accumulate;
+};
+
+template <int C>
+struct BwdNhwcCfg {
+  static constexpr bool kResidentD = (C <= 128);
+  static constexpr int kFBytes = 128 * ROW_BYTES;                       // 16 KB: 128 positions x 32 channels
+  static constexpr int kDChunkBytes = C * ROW_BYTES;                    // C rows x 32 k
+  static constexpr int kStageBytes = kFBytes + (kResidentD ? 0 : kDChunkBytes);
+  static constexpr int kStages = (C == 512) ? 2 : (C == 256 ? 4 : 6);
+  static constexpr int kDResBytes = kResidentD ? C * C * 4 : 0;
+  static constexpr int kAccBufs = (C == 512) ? 1 : 2;
+  static constexpr int kTmemCols = (C == 64) ? 128 : (C == 128 ? 256 : 512);
+  static constexpr int kUmmaN = (C <= 256) ? C : 256;
+  static constexpr int kDBoxRows = (C <= 256) ? C : 256;
+  static constexpr int kOutBytes = 4 * 2 * 4096;                        // per epilogue warp: two 32 x 32 fp32 blocks
+  static constexpr int kSmemBytes = kStages * kStageBytes + kDResBytes + kOutBytes + 1024 + 256;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+// warp 0: TMA loads, warp 1: MMA + TMEM, warps 2..5: converters, warps 6..9: epilogue + TMA stores.
+template <int C>
+__global__ void __launch_bounds__(320, 1) gram_bwd_nhwc_tc_kernel(const __grid_constant__ CUtensorMap tmapF,
+                                                                 const __grid_constant__ CUtensorMap tmapD,
+                                                                 const __grid_constant__ CUtensorMap tmapO,
+                                                                 const __grid_constant__ BwdNhwcParams P) {
+  using Cfg = BwdNhwcCfg<C>;
+  constexpr int S = Cfg::kStages;
+  constexpr int KC = C / BK;            // K chunks per tile
+  constexpr int NB = Cfg::kAccBufs;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* dres = smem + S * Cfg::kStageBytes;
+  uint8_t* ostage = dres + Cfg::kDResBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + Cfg::kOutBytes);
+  // full[S] conv[S] empty[S] acc_full[2] acc_empty[2] d_full d_conv
+  const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + S), bar_empty = smem_u32(bars + 2 * S),
+                 bar_accf = smem_u32(bars + 3 * S), bar_acce = smem_u32(bars + 3 * S + 2),
+                 bar_dfull = smem_u32(bars + 3 * S + 4), bar_dconv = smem_u32(bars + 3 * S + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 6);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_tiles = ((int)blockIdx.x < P.n_tiles) ? (P.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmapF);
+    prefetch_tmap(&tmapD);
+    prefetch_tmap(&tmapO);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, 128);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_accf + 8 * b, 1);
+      mbar_init(bar_acce + 8 * b, 128);
+    }
+    mbar_init(bar_dfull, 1);
+    mbar_init(bar_dconv, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      if (Cfg::kResidentD) {
+        mbar_arrive_expect_tx(bar_dfull, (uint32_t)Cfg::kDResBytes);
+        for (int kc = 0; kc < KC; ++kc)
+          tma_load_2d(smem_u32(dres + kc * Cfg::kDChunkBytes), &tmapD, bar_dfull, kc * BK, 0);
+      }
+      int it = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int64_t n0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * 128;
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)Cfg::kStageBytes);
+          const uint32_t dst = smem_u32(smem + s * Cfg::kStageBytes);
+          tma_load_2d(dst, &tmapF, bar_full + 8 * s, kc * BK, (int)n0);
+          if (!Cfg::kResidentD) {
+            tma_load_2d(dst + Cfg::kFBytes, &tmapD, bar_full + 8 * s, kc * BK, 0);
+            if (C == 512) tma_load_2d(dst + Cfg::kFBytes + 256 * ROW_BYTES, &tmapD, bar_full + 8 * s, kc * BK, 256);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_tf32(128, Cfg::kUmmaN, 0, 0);
+      if (Cfg::kResidentD) {
+        mbar_wait(bar_dconv, 0);
+        tc_fence_after();
+      }
+      int it = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int b = ti % NB;
+        const uint32_t bph = (uint32_t)(ti / NB) & 1u;
+        mbar_wait(bar_acce + 8 * b, bph ^ 1u);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + b * C;
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(bar_conv + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t f_base = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t d_base = Cfg::kResidentD ? smem_u32(dres + kc * Cfg::kDChunkBytes) : f_base + Cfg::kFBytes;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint32_t acc = (kc > 0 || k > 0) ? 1u : 0u;
+            const uint64_t ad = umma_desc_sw128(f_base + k * 32, 16, 1024);
+            umma_tf32(d_tmem, ad, umma_desc_sw128(d_base + k * 32, 16, 1024), idesc, acc);
+            if (C == 512)
+              umma_tf32(d_tmem + 256, ad, umma_desc_sw128(d_base + 256 * ROW_BYTES + k * 32, 16, 1024), idesc, acc);
+          }
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_accf + 8 * b);
+      }
+    }
+  } else if (warp < 6) {
+    // ===== converters =====
+    const int ctid = threadIdx.x - 64;
+    if (Cfg::kResidentD) {
+      mbar_wait(bar_dfull, 0);
+      convert_tf32_inplace(dres, Cfg::kDResBytes, ctid);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_dconv);
+    }
+    const int total = my_tiles * KC;
+    for (int it = 0; it < total; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (uint32_t)(it / S) & 1u;
+      mbar_wait(bar_full + 8 * s, ph);
+      convert_tf32_inplace(smem + s * Cfg::kStageBytes, Cfg::kStageBytes, ctid);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_conv + 8 * s);
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> swizzled shared block -> TMA store / reduce-add =====
+    const int sub = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(sub * 32) << 16);
+    const float scale = P.gscale ? P.scale * __ldg(P.gscale) : P.scale;
+    const uint32_t stg = smem_u32(ostage + (warp - 6) * 8192);
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    uint32_t v[32];
+    uint32_t nbuf = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int b = ti % NB;
+      const uint32_t bph = (uint32_t)(ti / NB) & 1u;
+      const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * 128 + sub * 32;
+      mbar_wait(bar_accf + 8 * b, bph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < C / 32; ++g) {
+        tmem_ld_x32(lane_addr + b * C + g * 32, v);
+        tmem_ld_wait();
+        if (lane == 0) tma_store_wait_read<1>();    // the block stored two rounds ago has left shared memory
+        __syncwarp();
+        const uint32_t buf = stg + (nbuf & 1u) * 4096u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = buf + row_off + ((((uint32_t)j) ^ sw) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                       "f"(scale * __uint_as_float(v[4 * j])), "f"(scale * __uint_as_float(v[4 * j + 1])),
+                       "f"(scale * __uint_as_float(v[4 * j + 2])), "f"(scale * __uint_as_float(v[4 * j + 3]))
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && p0 < P.HW) {
+          if (P.accumulate) tma_reduce_add_2d(&tmapO, buf, g * 32, (int)p0);
+          else tma_store_2d(&tmapO, buf, g * 32, (int)p0);
+          tma_store_commit();
+        }
+        ++nbuf;
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acce + 8 * b);
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
 bool gram_tc_supported(int C, int64_t HW, const void* F) {
@@ -503,12 +797,13 @@ void gram_tc_plan(int C, int64_t HW, int num_sms, GramPlan* plan) {
   }
 }
 
-template <int C>
+template <int C, int NU, int G, bool NHWC>
 static int launch_fwd(const float* F, int64_t HW, int64_t ld, float* partials, const GramPlan& plan,
                       cudaStream_t stream) {
-  using Cfg = FwdCfg<C>;
+  using Cfg = FwdCfg<C, NU, G>;
   CUtensorMap tmap;
-  int rc = make_tmap(&tmap, F, C, HW, ld, Cfg::kBoxRows);
+  int rc = NHWC ? make_tmap_nhwc_strips(&tmap, F, C, HW, (C == 64) ? 2 : (C == 128 ? 4 : 8))
+                : make_tmap(&tmap, F, C, HW, ld, Cfg::kBoxRows);
   if (rc != AST_OK) return rc;
   FwdParams P;
   P.HW = HW;
@@ -525,24 +820,55 @@ static int launch_fwd(const float* F, int64_t HW, int64_t ld, float* partials, c
   }
   P.cta_off[plan.n_tiles] = off;
   P.partials = partials;
-  cudaError_t e = cudaFuncSetAttribute(gram_fwd_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  static const int noround = (getenv("AST_GRAM_FWD_NOROUND") && atoi(getenv("AST_GRAM_FWD_NOROUND")) == 1) ? 1 : 0;
+  P.skip_rounding = noround;
+  cudaError_t e = cudaFuncSetAttribute(gram_fwd_tc_kernel<C, NU, G, NHWC>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("gram_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return AST_ERR_CUDA;
   }
-  gram_fwd_tc_kernel<C><<<off, 192, Cfg::kSmemBytes, stream>>>(tmap, P);
+  gram_fwd_tc_kernel<C, NU, G, NHWC><<<off, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmap, P);
   return check_launch("gram_fwd_tc");
 }
 
-int gram_tc_fwd(const float* F, int C, int64_t HW, int64_t ld, float* partials, const GramPlan& plan, int num_sms,
-                cudaStream_t stream) {
-  (void)num_sms;
-  switch (C) {
-    case 64: return launch_fwd<64>(F, HW, ld, partials, plan, stream);
-    case 128: return launch_fwd<128>(F, HW, ld, partials, plan, stream);
-    case 256: return launch_fwd<256>(F, HW, ld, partials, plan, stream);
-    case 512: return launch_fwd<512>(F, HW, ld, partials, plan, stream);
+// Pipeline shape of the forward kernel: (units per stage, converter groups).  AST_GRAM_FWD_CFG="NU,G" overrides
+// the per-C default for tuning sweeps (tests/tools/gram_sweep.py); every shape gives bit-identical results
+// because the accumulation order inside a CTA does not depend on it.
+static void fwd_cfg(int C, int* nu, int* g) {
+  static int env_nu = -1, env_g = -1;
+  if (env_nu < 0) {
+    int a = 0, b = 0;
+    const char* e = getenv("AST_GRAM_FWD_CFG");
+    if (e && sscanf(e, "%d,%d", &a, &b) == 2 && (a == 1 || a == 2) && (b == 1 || b == 2)) {
+      env_g = b;
+      env_nu = a;
+    } else {
+      env_g = 0;
+      env_nu = 0;
+    }
   }
+  // measured on B200 (profiles/r01_fwd_cfg_sweep.log): the four shapes are within 1 % of one another, so the
+  // smallest one is the default
+  *nu = env_nu ? env_nu : 1;
+  *g = env_g ? env_g : 1;
+  if (C >= 256) *nu = 1;   // a stage already holds 32/64 KB
+}
+
+int gram_tc_fwd(const float* F, int C, int64_t HW, int64_t ld, int nhwc, float* partials, const GramPlan& plan,
+                int num_sms, cudaStream_t stream) {
+  (void)num_sms;
+  int nu, g;
+  fwd_cfg(C, &nu, &g);
+#define AST_FWD_CASE(CC, NN, GG)                                                                   \
+  if (C == CC && nu == NN && g == GG)                                                              \
+    return nhwc ? launch_fwd<CC, NN, GG, true>(F, HW, ld, partials, plan, stream)                  \
+                : launch_fwd<CC, NN, GG, false>(F, HW, ld, partials, plan, stream);
+  AST_FWD_CASE(64, 1, 1) AST_FWD_CASE(64, 1, 2) AST_FWD_CASE(64, 2, 1) AST_FWD_CASE(64, 2, 2)
+  AST_FWD_CASE(128, 1, 1) AST_FWD_CASE(128, 1, 2) AST_FWD_CASE(128, 2, 1) AST_FWD_CASE(128, 2, 2)
+  AST_FWD_CASE(256, 1, 1) AST_FWD_CASE(256, 1, 2)
+  AST_FWD_CASE(512, 1, 1) AST_FWD_CASE(512, 1, 2)
+#undef AST_FWD_CASE
   set_error("gram_tc_fwd: unsupported C=%d", C);
   return AST_ERR_UNSUPPORTED;
 }
@@ -584,6 +910,46 @@ int gram_tc_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, f
     case 512: return launch_bwd<512>(D, F, HW, ld, scale, gscale, dF, accumulate, num_sms, stream);
   }
   set_error("gram_tc_bwd: unsupported C=%d", C);
+  return AST_ERR_UNSUPPORTED;
+}
+
+template <int C>
+static int launch_bwd_nhwc(const float* D, const float* F, int64_t HW, float scale, const float* gscale, float* dF,
+                           int accumulate, int num_sms, cudaStream_t stream) {
+  using Cfg = BwdNhwcCfg<C>;
+  CUtensorMap tmF, tmD, tmO;
+  int rc = make_tmap(&tmF, F, (uint64_t)HW, C, C, 128);
+  if (rc != AST_OK) return rc;
+  rc = make_tmap(&tmD, D, C, C, C, Cfg::kDBoxRows);
+  if (rc != AST_OK) return rc;
+  rc = make_tmap(&tmO, dF, (uint64_t)HW, C, C, 32);
+  if (rc != AST_OK) return rc;
+  BwdNhwcParams P;
+  P.HW = HW;
+  P.n_tiles = (int)((HW + 127) / 128);
+  P.scale = scale;
+  P.gscale = gscale;
+  P.accumulate = accumulate;
+  cudaError_t e = cudaFuncSetAttribute(gram_bwd_nhwc_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes);
+  if (e != cudaSuccess) {
+    set_error("gram_tc_bwd_nhwc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return AST_ERR_CUDA;
+  }
+  const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
+  gram_bwd_nhwc_tc_kernel<C><<<grid, 320, Cfg::kSmemBytes, stream>>>(tmF, tmD, tmO, P);
+  return check_launch("gram_bwd_nhwc_tc");
+}
+
+int gram_tc_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale, float* dF,
+                     int accumulate, int num_sms, cudaStream_t stream) {
+  switch (C) {
+    case 64: return launch_bwd_nhwc<64>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
+    case 128: return launch_bwd_nhwc<128>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
+    case 256: return launch_bwd_nhwc<256>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
+    case 512: return launch_bwd_nhwc<512>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
+  }
+  set_error("gram_tc_bwd_nhwc: unsupported C=%d", C);
   return AST_ERR_UNSUPPORTED;
 }
 

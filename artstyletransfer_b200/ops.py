@@ -67,7 +67,7 @@ class KernelStats:
 STATS = KernelStats()
 
 # kernels launched per C-ABI entry point
-_KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_finalize': 1, 'ast_gram_bwd': 1, 'ast_mse_fwd': 1, 'ast_mse_bwd': 1,
+_KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_mse_fwd_nhwc': 2, 'ast_gram_bwd_nhwc': 1, 'ast_gram_finalize': 1, 'ast_gram_bwd': 1, 'ast_mse_fwd': 1, 'ast_mse_bwd': 1,
                      'ast_tv_fwd': 1, 'ast_tv_bwd': 1, 'ast_level_combine': 1, 'ast_bicubic_down2x': 1,
                      'ast_bicubic_down2x_adj': 1, 'ast_bicubic_resize': 1, 'ast_bicubic_resize_adj': 1,
                      'ast_noise_init': 1}
@@ -185,6 +185,21 @@ def gram_bwd(D: torch.Tensor, feat: torch.Tensor, C: int, HW: int, scale: float,
     _launch(feat.device, ('gram_bwd', C, HW, precision), 'ast_gram_bwd', D.data_ptr(), feat.data_ptr() + 4 * offset, C,
             HW, HW if ld is None else ld, scale, gscale.data_ptr() if gscale is not None else None,
             dF.data_ptr() + 4 * offset, int(accumulate), precision)
+
+
+def gram_mse_fwd_nhwc(feat: torch.Tensor, C: int, HW: int, scale: float, target: Optional[torch.Tensor],
+                      out: torch.Tensor, loss: Optional[torch.Tensor], ws: Workspace, offset: int = 0) -> None:
+    """feat: (HW, C) row-major storage (torch channels_last); the operand starts `offset` elements in."""
+    _launch(feat.device, ('gram_fwd_nhwc', C, HW), 'ast_gram_mse_fwd_nhwc', feat.data_ptr() + 4 * offset, C, HW, scale,
+            target.data_ptr() if target is not None else None, out.data_ptr(),
+            loss.data_ptr() if loss is not None else None, ws.ptr, ws.nbytes)
+
+
+def gram_bwd_nhwc(D: torch.Tensor, feat: torch.Tensor, C: int, HW: int, scale: float, gscale: Optional[torch.Tensor],
+                  dF: torch.Tensor, accumulate: bool, offset: int = 0) -> None:
+    _launch(feat.device, ('gram_bwd_nhwc', C, HW, int(accumulate)), 'ast_gram_bwd_nhwc', D.data_ptr(),
+            feat.data_ptr() + 4 * offset, C, HW, scale, gscale.data_ptr() if gscale is not None else None,
+            dF.data_ptr() + 4 * offset, int(accumulate))
 
 
 def _gscale(g: Optional[torch.Tensor], dev: torch.device) -> Optional[torch.Tensor]:

@@ -85,6 +85,16 @@ int ast_gram_finalize(const float* G_raw, int C, float scale, const float* A, fl
 int ast_gram_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, float scale,
                  const float* gscale, float* dF, int accumulate, int precision, void* stream);
 
+/* Same two operations for a feature map held as (HW, C) row-major — torch channels_last, the layout in which
+ * cuDNN's TF32 convolutions run without NCHW<->NHWC transposes (profiles/r01_vgg_layout.md).  C in
+ * {64,128,256,512}, any HW, dense rows (a row band of an NHWC map is a contiguous range of positions: offset the
+ * pointer).  TF32 operands only.  out/loss/ws as for ast_gram_mse_fwd; dF may alias nothing else.
+ * accumulate != 0 adds into dF with TMA reduce-add (the SM never reads dF). */
+int ast_gram_mse_fwd_nhwc(const float* F, int C, int64_t HW, float scale, const float* A, float* out,
+                          float* loss, void* ws, size_t ws_bytes, void* stream);
+int ast_gram_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale,
+                      const float* gscale, float* dF, int accumulate, void* stream);
+
 /* ---- Content MSE (neural_style_transfer.py:95) ---------------------------------------------
  *   *loss = scale * sum((X - T)^2)      (scale = 1/n for MSELoss(reduction='mean'))
  *   dX (+)= scale * (X - T)             (scale = 2 * content_weight / n * upstream)       */
@@ -93,6 +103,24 @@ int ast_mse_fwd(const float* X, const float* T, int64_t n, float scale, float* l
                 size_t ws_bytes, void* stream);
 int ast_mse_bwd(const float* X, const float* T, int64_t n, float scale, const float* gscale,
                 float* dX, int accumulate, void* stream);
+
+/* ---- Glue between the cuDNN convolutions of the VGG19 feature path (neural_nets.py:53-68) --------------
+ * Activations are (H, W, C) row-major (torch channels_last), C % 4 == 0, 16-byte aligned.  The convolutions
+ * themselves stay on cuDNN; these replace the bias add, ReLU(inplace), max_pool2d (+ its int64 indices) and
+ * their autograd backward kernels, which are 40 % of the reference's closure on a B200.
+ *   ast_bias_relu_nhwc      : y[p,c] = max(y[p,c] + bias[c], 0) in place
+ *   ast_relu_bwd            : g[i] = r[i] > 0 ? g[i] : 0 in place (r = ReLU output)
+ *   ast_maxpool2x2_nhwc     : 2x2 / stride 2 max, floor mode (y is (H/2, W/2, C))
+ *   ast_maxpool2x2_bwd_nhwc : gx = gy routed to the window's first maximum (torch's tie rule); relu_mask != 0 also
+ *                             applies the backward of the ReLU that produced x (x > 0), fusing two torch kernels
+ *   ast_chw_to_hwc / ast_hwc_to_chw : (C, HW) planar <-> (HW, C) interleaved for C <= 16 (the image, its gradient) */
+int ast_bias_relu_nhwc(float* y, const float* bias, int C, int64_t n_pos, void* stream);
+int ast_relu_bwd(float* g, const float* r, int64_t n, void* stream);
+int ast_maxpool2x2_nhwc(const float* x, int C, int H, int W, float* y, void* stream);
+int ast_maxpool2x2_bwd_nhwc(const float* gy, const float* x, int C, int H, int W, int relu_mask,
+                            float* gx, void* stream);
+int ast_chw_to_hwc(const float* x, int C, int64_t HW, float* y, void* stream);
+int ast_hwc_to_chw(const float* x, int C, int64_t HW, float* y, int accumulate, void* stream);
 
 /* ---- Total variation (math_utils.py:37-41) -------------------------------------------------
  *   sums[0] = sum |y[..., :-1] - y[..., 1:]|,  sums[1] = sum |y[:, :-1, :] - y[:, 1:, :]|
