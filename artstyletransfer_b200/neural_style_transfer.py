@@ -24,7 +24,7 @@ from torch import Tensor
 from torch.autograd import Variable
 from torch.optim import Adam, LBFGS
 
-from . import math_utils, ops
+from . import feature_path, math_utils, ops
 from . import parallel as _parallel
 
 # ImageNet statistics (:22-23)
@@ -39,6 +39,10 @@ IGNORE_GRADIENT_MAP_JUST_FOR_DEMONSTRATION = False
 
 VERBOSE = False                 # True restores the reference's per-closure prints (adds host syncs)
 PRECISION = None                # None -> ops.DEFAULT_PRECISION ('tf32'); 'fp32' for the exact path
+# True: a level runs as the explicit channels-last schedule of feature_path.py (cuDNN convs without layout
+# transposes + this library's glue and (HW, C) Gram kernels).  False: torch modules + autograd around the NCHW
+# kernels (also what 'fp32' precision and non-Vgg19 feature nets use).
+CHANNELS_LAST_PATH = os.environ.get('AST_CHANNELS_LAST', '1') != '0'
 
 
 class ContentStylePair:
@@ -91,6 +95,9 @@ class LossBuilder:
             del style_rep_builder
         self.__target_grams = [g[0].detach().contiguous() for g in self.__target_style_representation]
         self.__wss = ops.LevelWorkspaces()
+        # channels-last schedule: targets are rebuilt through the same path on first use
+        self.__target_images = (target_content_image, target_style_image)
+        self.__path_targets = None
         self.shard = None                   # set by parallel.maybe_shard for row-band sharded levels
         self.replicated_rank0_only = False  # sharding on, level not shardable: ranks != 0 evaluate without grad
 
@@ -102,12 +109,33 @@ class LossBuilder:
     def target_style_representation(self):
         return self.__target_style_representation
 
+    def __path_plan(self, optimizing_img):
+        """The channels-last plan when this level can use it: TF32 Gram operands, a frozen Vgg19 on CUDA, batch 1."""
+        if not CHANNELS_LAST_PATH or ops._prec(PRECISION) != ops.L.AST_PREC_TF32:
+            return None
+        if not (torch.is_tensor(optimizing_img) and optimizing_img.is_cuda and optimizing_img.dim() == 4
+                and optimizing_img.shape[0] == 1 and optimizing_img.dtype == torch.float32):
+            return None
+        if isinstance(self.__style_feature_maps_indices, int) or isinstance(self.__content_feature_maps_index, list):
+            return None
+        return feature_path.plan_for(self.__neural_net)
+
     def build(self, optimizing_img):
         if self.shard is not None:
             return self.shard.build(optimizing_img)
         if self.replicated_rank0_only and torch.is_grad_enabled():
             with torch.no_grad():
                 return self.build(optimizing_img)
+        plan = self.__path_plan(optimizing_img)
+        if plan is not None:
+            if self.__path_targets is None:
+                self.__path_targets = feature_path.build_targets(
+                    plan, self.__target_images[0], self.__target_images[1], self.__content_feature_maps_index,
+                    self.__style_feature_maps_indices, self.__wss)
+            cfg = (plan, self.__path_targets, self.__content_feature_maps_index,
+                   tuple(self.__style_feature_maps_indices),
+                   (self.__content_weight, self.__style_weight, self.__tv_weight), self.__wss)
+            return feature_path.LevelPathFn.apply(cfg, optimizing_img)
         feats = self.__neural_net(optimizing_img)
         cfg = (self.__target_content_representation, self.__target_grams,
                (self.__content_weight, self.__style_weight, self.__tv_weight), self.__wss, ops._prec(PRECISION))

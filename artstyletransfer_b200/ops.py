@@ -70,7 +70,8 @@ STATS = KernelStats()
 _KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_mse_fwd_nhwc': 2, 'ast_gram_bwd_nhwc': 1, 'ast_gram_finalize': 1, 'ast_gram_bwd': 1, 'ast_mse_fwd': 1, 'ast_mse_bwd': 1,
                      'ast_tv_fwd': 1, 'ast_tv_bwd': 1, 'ast_level_combine': 1, 'ast_bicubic_down2x': 1,
                      'ast_bicubic_down2x_adj': 1, 'ast_bicubic_resize': 1, 'ast_bicubic_resize_adj': 1,
-                     'ast_noise_init': 1}
+                     'ast_noise_init': 1, 'ast_bias_relu_nhwc': 1, 'ast_relu_bwd': 1, 'ast_maxpool2x2_nhwc': 1,
+                     'ast_maxpool2x2_bwd_nhwc': 1, 'ast_chw_to_hwc': 1, 'ast_hwc_to_chw': 1}
 
 
 def _launch(dev: torch.device, key, name: str, *args) -> None:
@@ -208,6 +209,38 @@ def _gscale(g: Optional[torch.Tensor], dev: torch.device) -> Optional[torch.Tens
     if g.dtype != torch.float32 or g.device != dev or not g.is_contiguous():
         g = g.to(device=dev, dtype=torch.float32).contiguous()
     return g
+
+
+# ------------------------------------------------------------------------------------------------------
+# glue around the cuDNN convolutions (csrc/vgg_glue.cu); tensors are torch channels_last (1, C, H, W)
+# ------------------------------------------------------------------------------------------------------
+def bias_relu_(y: torch.Tensor, bias: torch.Tensor) -> None:
+    c = y.shape[1]
+    _launch(y.device, ('bias_relu', c, y.numel()), 'ast_bias_relu_nhwc', y.data_ptr(), bias.data_ptr(), c,
+            y.numel() // c)
+
+
+def relu_bwd_(g: torch.Tensor, r: torch.Tensor) -> None:
+    _launch(g.device, ('relu_bwd', g.numel()), 'ast_relu_bwd', g.data_ptr(), r.data_ptr(), g.numel())
+
+
+def maxpool2x2(x: torch.Tensor, y: torch.Tensor) -> None:
+    _, c, h, w = x.shape
+    _launch(x.device, ('maxpool', c, h, w), 'ast_maxpool2x2_nhwc', x.data_ptr(), c, h, w, y.data_ptr())
+
+
+def maxpool2x2_bwd(gy: torch.Tensor, x: torch.Tensor, gx: torch.Tensor, relu_mask: bool) -> None:
+    _, c, h, w = x.shape
+    _launch(x.device, ('maxpool_bwd', c, h, w), 'ast_maxpool2x2_bwd_nhwc', gy.data_ptr(), x.data_ptr(), c, h, w,
+            int(relu_mask), gx.data_ptr())
+
+
+def chw_to_hwc(x: torch.Tensor, y: torch.Tensor, c: int, hw: int) -> None:
+    _launch(x.device, ('chw_to_hwc', c, hw), 'ast_chw_to_hwc', x.data_ptr(), c, hw, y.data_ptr())
+
+
+def hwc_to_chw(x: torch.Tensor, y: torch.Tensor, c: int, hw: int, accumulate: bool) -> None:
+    _launch(x.device, ('hwc_to_chw', c, hw), 'ast_hwc_to_chw', x.data_ptr(), c, hw, y.data_ptr(), int(accumulate))
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -166,6 +166,24 @@ def kernel_work(key):
     if k in ('down2x', 'down2x_adj'):
         _, c, h, w = key
         return 4.0 * c * (h * w + h * w / 4), 0.0
+    if k == 'gram_fwd_nhwc':
+        _, c, hw = key
+        return 4.0 * c * hw + 8.0 * c * c, 2.0 * c * c * hw
+    if k == 'gram_bwd_nhwc':
+        _, c, hw, acc = key
+        return (12.0 if acc else 8.0) * c * hw + 4.0 * c * c, 2.0 * c * c * hw
+    if k == 'bias_relu':
+        return 8.0 * key[2], 0.0            # read + write the activation in place
+    if k == 'relu_bwd':
+        return 12.0 * key[1], 0.0           # read g, read r, write g
+    if k == 'maxpool':
+        _, c, h, w = key
+        return 4.0 * c * (h * w + (h // 2) * (w // 2)), 0.0
+    if k == 'maxpool_bwd':
+        _, c, h, w = key
+        return 4.0 * c * (2 * h * w + (h // 2) * (w // 2)), 0.0
+    if k in ('chw_to_hwc', 'hwc_to_chw'):
+        return 8.0 * key[1] * key[2], 0.0
     return 0.0, 0.0
 
 
@@ -330,7 +348,7 @@ def run_ours(args):
                    'closures_timed': closures, 'gram_operands': args.precision or ops.DEFAULT_PRECISION,
                    'vgg_convs': 'torch/cuDNN (out of scope)'},
         'clocks': clk, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,
-        'kernels': table[:14], 'own_kernels_ms_per_step': round(ours_ms / max(closures, 1), 3),
+        'kernels': table[:20], 'own_kernels_ms_per_step': round(ours_ms / max(closures, 1), 3),
         'init_image_s': round(init_s, 4), 'loss_after': loss_now,
     }
     if world == 1 and not args.no_cpu_baseline:
