@@ -109,6 +109,13 @@ class LossBuilder:
     def target_style_representation(self):
         return self.__target_style_representation
 
+    @property
+    def target_images(self):
+        return self.__target_images
+
+    def path_plan(self, optimizing_img):
+        return self.__path_plan(optimizing_img)
+
     def __path_plan(self, optimizing_img):
         """The channels-last plan when this level can use it: TF32 Gram operands, a frozen Vgg19 on CUDA, batch 1."""
         if not CHANNELS_LAST_PATH or ops._prec(PRECISION) != ops.L.AST_PREC_TF32:

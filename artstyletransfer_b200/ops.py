@@ -71,7 +71,7 @@ _KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_mse_fwd_nhwc': 2, 'ast_gra
                      'ast_tv_fwd': 1, 'ast_tv_bwd': 1, 'ast_level_combine': 1, 'ast_bicubic_down2x': 1,
                      'ast_bicubic_down2x_adj': 1, 'ast_bicubic_resize': 1, 'ast_bicubic_resize_adj': 1,
                      'ast_noise_init': 1, 'ast_bias_relu_nhwc': 1, 'ast_relu_bwd': 1, 'ast_maxpool2x2_nhwc': 1,
-                     'ast_maxpool2x2_bwd_nhwc': 1, 'ast_chw_to_hwc': 1, 'ast_hwc_to_chw': 1}
+                     'ast_maxpool2x2_bwd_nhwc': 1, 'ast_chw_to_hwc': 1, 'ast_hwc_to_chw': 1, 'ast_add_rows': 1}
 
 
 def _launch(dev: torch.device, key, name: str, *args) -> None:
@@ -235,12 +235,27 @@ def maxpool2x2_bwd(gy: torch.Tensor, x: torch.Tensor, gx: torch.Tensor, relu_mas
             int(relu_mask), gx.data_ptr())
 
 
-def chw_to_hwc(x: torch.Tensor, y: torch.Tensor, c: int, hw: int) -> None:
-    _launch(x.device, ('chw_to_hwc', c, hw), 'ast_chw_to_hwc', x.data_ptr(), c, hw, y.data_ptr())
+def chw_to_hwc(x: torch.Tensor, y: torch.Tensor, c: int, hw: int, plane: Optional[int] = None, x_off: int = 0,
+               y_off: int = 0) -> None:
+    """planar -> interleaved; offsets in elements, `plane` = stride between the planar side's channel planes."""
+    _launch(x.device, ('chw_to_hwc', c, hw), 'ast_chw_to_hwc', x.data_ptr() + 4 * x_off, c, hw,
+            hw if plane is None else plane, y.data_ptr() + 4 * y_off)
 
 
-def hwc_to_chw(x: torch.Tensor, y: torch.Tensor, c: int, hw: int, accumulate: bool) -> None:
-    _launch(x.device, ('hwc_to_chw', c, hw), 'ast_hwc_to_chw', x.data_ptr(), c, hw, y.data_ptr(), int(accumulate))
+def hwc_to_chw(x: torch.Tensor, y: torch.Tensor, c: int, hw: int, accumulate: bool, plane: Optional[int] = None,
+               x_off: int = 0, y_off: int = 0) -> None:
+    _launch(x.device, ('hwc_to_chw', c, hw), 'ast_hwc_to_chw', x.data_ptr() + 4 * x_off, c, hw,
+            y.data_ptr() + 4 * y_off, hw if plane is None else plane, int(accumulate))
+
+
+def add_rows(dst_a: Optional[torch.Tensor], src_a: Optional[torch.Tensor], dst_b: Optional[torch.Tensor],
+             src_b: Optional[torch.Tensor]) -> None:
+    """dst_a += src_a; dst_b += src_b (contiguous rows of equal length; a pair may be None)."""
+    ref = dst_a if dst_a is not None else dst_b
+    if ref is None:
+        return
+    p = lambda t: t.data_ptr() if t is not None else None
+    _launch(ref.device, ('add_rows', ref.numel()), 'ast_add_rows', p(dst_a), p(src_a), p(dst_b), p(src_b), ref.numel())
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -1,5 +1,10 @@
 """Row-band sharding of the pyramid levels across the GPUs of one box.
 
+Two schemes.  The default (sharded_path.ShardedPathLevel, channels-last feature path) gives every rank exactly its
+band of rows and exchanges ONE halo row with each neighbour before every 3x3 convolution (and the mirrored
+gradient rows in the backward) — no redundant convolution work.  The older scheme below (ShardedLevel, torch
+modules + autograd, used for fp32 precision) pads the band with an 80-row halo instead and crops.
+
 One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Every rank holds the full optimizing
 image and an identical optimizer.  Per level and closure each rank
   1. runs VGG19 (torch/cuDNN) on its band of rows plus an 80-row halo on interior sides (the receptive field
@@ -69,6 +74,51 @@ class TorchDistGroup:
 
     def all_reduce_sum(self, t: torch.Tensor) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def exchange(self, sends, recvs) -> None:
+        """One grouped point-to-point step: sends / recvs are lists of (contiguous tensor, peer rank).  Over NCCL
+        this is a single ncclGroup (one kernel moving every row over NVLink); the wait orders the current stream
+        after it without blocking the host."""
+        p2p = [dist.P2POp(dist.isend, t, peer) for t, peer in sends] + \
+              [dist.P2POp(dist.irecv, t, peer) for t, peer in recvs]
+        if not p2p:
+            return
+        for work in dist.batch_isend_irecv(p2p):
+            work.wait()
+
+
+def halo_exchange_fwd(group, rows: torch.Tensor) -> None:
+    """rows: (h + 2, w, C) contiguous view of a padded activation band (row 0 and row h+1 are the halos).
+    Sends the first / last owned row to the rank above / below and receives their edge rows into the halos.
+    Halos at the image border are left alone (they hold the convolution's zero padding)."""
+    h = rows.shape[0] - 2
+    up, dn = group.rank - 1, group.rank + 1
+    sends, recvs = [], []
+    if up >= 0:
+        sends.append((rows[1], up))
+        recvs.append((rows[0], up))
+    if dn < group.world:
+        sends.append((rows[h], dn))
+        recvs.append((rows[h + 1], dn))
+    group.exchange(sends, recvs)
+
+
+def halo_exchange_bwd(group, rows: torch.Tensor, scratch: torch.Tensor, add_rows) -> None:
+    """Adjoint of halo_exchange_fwd on a padded gradient band: the halo rows hold gradient that belongs to the
+    neighbours' edge rows.  Sends them over, receives the neighbours' halo gradients into scratch (2, w, C) and
+    adds them to the first / last owned row with add_rows(dst_a, src_a, dst_b, src_b)."""
+    h = rows.shape[0] - 2
+    up, dn = group.rank - 1, group.rank + 1
+    sends, recvs = [], []
+    if up >= 0:
+        sends.append((rows[0], up))
+        recvs.append((scratch[0], up))
+    if dn < group.world:
+        sends.append((rows[h + 1], dn))
+        recvs.append((scratch[1], dn))
+    group.exchange(sends, recvs)
+    add_rows(rows[1] if up >= 0 else None, scratch[0] if up >= 0 else None,
+             rows[h] if dn < group.world else None, scratch[1] if dn < group.world else None)
 
 
 _GROUP = None     # set by init_sharding(); None -> single-process path
@@ -228,7 +278,14 @@ def maybe_shard(loss_builders, optimizing_img, neural_net, content_idx, style_id
     n = 0
     for i, lb in enumerate(loss_builders):
         lh, lw = h >> i, w >> i
-        if BandPlan.shardable(lh, _GROUP.world) and lw % ALIGN == 0 and (h % (1 << i) == 0):
+        ok = BandPlan.shardable(lh, _GROUP.world) and lw % ALIGN == 0 and (h % (1 << i) == 0)
+        plan = lb.path_plan(optimizing_img) if ok else None
+        if plan is not None:
+            from .sharded_path import ShardedPathLevel
+            lb.shard = ShardedPathLevel(_GROUP, plan, lb.target_images[0], lb.target_images[1], content_idx,
+                                        style_idx, weights, lh, lw)
+            n += 1
+        elif ok:
             grams = [g[0].detach().contiguous() for g in lb.target_style_representation]
             lb.shard = ShardedLevel(_GROUP, neural_net, content_idx, style_idx, lb.target_content_representation,
                                     grams, weights, lh, lw, ops._prec(nst.PRECISION))

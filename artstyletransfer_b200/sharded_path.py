@@ -1,0 +1,242 @@
+"""Row-band sharded level on the channels-last feature path, with per-layer halo exchange.
+
+Every rank owns hb = H / R image rows of the level (hb a multiple of 16, so the four 2x2 max-pools never straddle
+ranks) and ONLY computes those: before each 3x3 convolution it swaps one activation row with each neighbour
+(parallel.halo_exchange_fwd; rows are contiguous in NHWC, so they go over NVLink in place, no packing), and in the
+backward the gradient that the convolution's backward-data puts into the halo rows goes back to its owner
+(parallel.halo_exchange_bwd).  The first convolution needs no exchange in either direction: every rank holds the
+whole (3-channel) level image, and the per-closure all-reduce of the image gradient sums the halo rows' gradient.
+
+Per level and closure: 12 + 12 grouped send/recv steps (<= 0.8 MB each), ONE all-reduce(sum) of the packed raw
+Grams + content SSE (~2.4 MB), then every rank finalises identically.  Activations live in persistent padded
+buffers (row 0 / row h+1 are the halos; at the image border they stay zero = the convolution's zero padding).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+
+from . import feature_path as fp
+from . import ops
+from . import parallel as par
+
+_CL = torch.channels_last
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """(1, C, h, w) channels_last -> contiguous (h, w, C) view."""
+    return t.permute(0, 2, 3, 1)[0]
+
+
+class ShardedPathLevel:
+    """Replaces LossBuilder.build for one level when sharding is on (same return contract)."""
+
+    def __init__(self, group, plan: fp.FeaturePlan, content_img: torch.Tensor, style_img: torch.Tensor,
+                 content_idx: int, style_idx: Sequence[int], weights, height: int, width: int):
+        self.group, self.plan = group, plan
+        self.cidx, self.sidx = content_idx, list(style_idx)
+        self.weights = tuple(float(w) for w in weights)
+        self.H, self.W = height, width
+        self.band = par.BandPlan(height, group.rank, group.world, halo=0)
+        self.hb = self.band.r1 - self.band.r0
+        dev = content_img.device
+        self.wss = ops.LevelWorkspaces()
+        # targets: every rank runs the whole content / style image once at set-up (replicated, not on the hot path)
+        tg = fp.build_targets(plan, content_img, style_img, content_idx, style_idx, self.wss)
+        self.target_grams = tg.grams
+        cs = par.LAYER_STRIDE[content_idx]
+        crow = _rows(tg.content_cl)
+        self.target_content_band = crow[self.band.r0 // cs:self.band.r1 // cs].contiguous()
+        self.content_numel_global = tg.content_cl.numel()
+        self.channels = [g.shape[-1] for g in tg.grams]
+        self.offs, self.content_slot, self.n_packed = par.pack_layout(self.channels)
+        self.fin_ws = [ops.reduce_workspace(dev) for _ in self.sidx]
+        # persistent padded activation bands: xin (the image band) and one per step
+        c0 = plan.steps[0][3]
+        self.xin = torch.zeros((1, c0, self.hb + 2, width), dtype=torch.float32, device=dev).contiguous(memory_format=_CL)
+        self.bufs: List[torch.Tensor] = []
+        c, h, w = c0, self.hb, width
+        for sidx in range(plan.n_steps_needed):
+            st = plan.steps[sidx]
+            if st[0] == 'conv':
+                c = st[4]
+            else:
+                h, w = h // 2, w // 2
+            self.bufs.append(torch.zeros((1, c, h + 2, w), dtype=torch.float32, device=dev).contiguous(memory_format=_CL))
+        self.scratch = {}
+        self.generation = 0
+
+    def scratch_rows(self, w: int, c: int) -> torch.Tensor:
+        key = (w, c)
+        if key not in self.scratch:
+            self.scratch[key] = torch.empty((2, w, c), dtype=torch.float32, device=self.xin.device)
+        return self.scratch[key]
+
+    def build(self, level_img: torch.Tensor):
+        return ShardPathFn.apply(self, level_img)
+
+
+def _interior(buf: torch.Tensor) -> torch.Tensor:
+    return buf[:, :, 1:-1, :]
+
+
+def _conv_fwd_into(x_pad, w, out):
+    torch.ops.aten.cudnn_convolution.out(x_pad, w, [0, 1], [1, 1], [1, 1], 1, False, False,
+                                         torch.backends.cudnn.allow_tf32, out=out)
+
+
+def _conv_bwd_data_padded(g, x_pad, w):
+    gi = torch.ops.aten.convolution_backward(g, x_pad, w, None, [1, 1], [0, 1], [1, 1], False, [0, 0], 1,
+                                             [True, False, False])[0]
+    return gi if gi.is_contiguous(memory_format=_CL) else gi.contiguous(memory_format=_CL)
+
+
+class ShardPathFn(torch.autograd.Function):
+    """input: the full level image (every rank has it).  outputs as LevelPathFn; the returned image gradient is
+    this rank's contribution (its band rows +- 1, plus the TV gradient on rank 0) — summed by sync_image_grad."""
+
+    @staticmethod
+    def forward(ctx, sh: ShardedPathLevel, level_img):
+        out4, state = sharded_forward(sh, level_img)
+        if ctx.needs_input_grad[1]:
+            ctx.state = state
+        total, content, style, tv = out4[0], out4[1], out4[2], out4[3]
+        ctx.mark_non_differentiable(content, style, tv)
+        return total, content, style, tv
+
+    @staticmethod
+    def backward(ctx, g_total, g_content, g_style, g_tv):
+        state, ctx.state = ctx.state, None
+        return None, sharded_backward(state, g_total)
+
+
+def sharded_forward(sh: ShardedPathLevel, level_img: torch.Tensor):
+    """Forward schedule of one sharded level.  Returns (out4 = [total, content, style, tv], state for backward)."""
+    dev = ops._require_cuda(level_img)
+    plan, band, grp = sh.plan, sh.band, sh.group
+    cw, sw, tvw = sh.weights
+    level_img = level_img.contiguous()
+    H, W, hb = sh.H, sh.W, sh.hb
+    if tuple(level_img.shape) != (1, plan.steps[0][3], H, W):
+        raise ValueError(f'sharded level expects {(1, plan.steps[0][3], H, W)}; got {tuple(level_img.shape)}')
+    sh.generation += 1
+    # image band + one row above / below straight from the replicated image (rows outside the image stay 0)
+    lo, hi = max(band.r0 - 1, 0), min(band.r1 + 1, H)
+    c0 = level_img.shape[1]
+    ops.chw_to_hwc(level_img, sh.xin, c0, (hi - lo) * W, plane=H * W, x_off=lo * W,
+                   y_off=(lo - (band.r0 - 1)) * W * c0)
+    x = sh.xin
+    taps = [None] * len(plan.tap_step)
+    for sidx in range(plan.n_steps_needed):
+        st = plan.steps[sidx]
+        y = sh.bufs[sidx]
+        if st[0] == 'conv':
+            if sidx > 0:
+                par.halo_exchange_fwd(grp, _rows(x))
+            yi = _interior(y)
+            _conv_fwd_into(x, st[1], yi)
+            ops.bias_relu_(yi, st[2])
+        else:
+            ops.maxpool2x2(_interior(x), _interior(y))
+        for k in plan.taps_at.get(sidx, ()):
+            taps[k] = _interior(y)
+        x = y
+    # raw partial Grams + partial content SSE -> one all-reduce -> identical finalize on every rank
+    n_style = len(sh.sidx)
+    packed = torch.zeros(sh.n_packed, dtype=torch.float32, device=dev)
+    for j, k in enumerate(sh.sidx):
+        f = taps[k]
+        c, hw_band = f.shape[1], f.shape[2] * f.shape[3]
+        ops.gram_mse_fwd_nhwc(f, c, hw_band, 1.0, None, packed[sh.offs[j]:sh.offs[j] + c * c], None,
+                              sh.wss.for_gram(j, c, hw_band, dev))
+    xc = taps[sh.cidx]
+    ops.mse_fwd(xc, sh.target_content_band, 1.0, packed[sh.content_slot], sh.wss.for_reduce('content', dev))
+    grp.all_reduce_sum(packed)
+    vals = torch.empty(n_style + 2, dtype=torch.float32, device=dev)
+    out4 = torch.empty(4, dtype=torch.float32, device=dev)
+    ds = {}
+    for j, k in enumerate(sh.sidx):
+        c = sh.channels[j]
+        st_ = par.LAYER_STRIDE[k]
+        hw_global = (H // st_) * (W // st_)
+        d = torch.empty((c, c), dtype=torch.float32, device=dev)
+        ops.gram_finalize(packed[sh.offs[j]:sh.offs[j] + c * c], c, 1.0 / (c * hw_global), sh.target_grams[j], d,
+                          vals[j], sh.fin_ws[j])
+        ds[k] = (d, hw_global)
+    torch.mul(packed[sh.content_slot], 1.0 / sh.content_numel_global, out=vals[n_style])
+    sums2 = torch.empty(2, dtype=torch.float32, device=dev)
+    ops.tv_fwd(level_img, sums2, vals[n_style + 1], sh.wss.for_reduce('tv', dev))
+    ops._launch(dev, ('combine',), 'ast_level_combine', vals.data_ptr(), n_style, vals[n_style].data_ptr(),
+                vals[n_style + 1].data_ptr(), cw, sw, tvw, out4.data_ptr())
+    return out4, (sh, sh.generation, ds, level_img, sums2)
+
+
+def sharded_backward(state, g_total) -> torch.Tensor:
+    """Backward schedule: this rank's contribution to the level image's gradient (g_total: upstream scalar or None)."""
+    sh, generation, ds, level_img, sums2 = state
+    if generation != sh.generation:
+        raise RuntimeError('sharded level: backward() after a newer forward() of the same level — its activation '
+                           'bands are persistent buffers; run forward and backward of a closure back to back')
+    plan, band, grp = sh.plan, sh.band, sh.group
+    cw, sw, tvw = sh.weights
+    dev = level_img.device
+    gsc = ops._gscale(g_total, dev)
+    n = len(sh.sidx)
+    H, W = sh.H, sh.W
+
+    def tap_grad(k, tap, g):
+        acc = g is not None
+        if not acc:
+            g = torch.empty(tap.shape, dtype=torch.float32, device=dev).contiguous(memory_format=_CL)
+        c, hw_band = tap.shape[1], tap.shape[2] * tap.shape[3]
+        wrote = False
+        if k in ds:
+            d, hw_global = ds[k]
+            ops.gram_bwd_nhwc(d, tap, c, hw_band, (sw / n) * 4.0 / (float(c) * c * c * hw_global), gsc, g, acc)
+            wrote = True
+        if k == sh.cidx:
+            ops.mse_bwd(tap, sh.target_content_band, cw * 2.0 / sh.content_numel_global, gsc, g, acc or wrote)
+            wrote = True
+        if not wrote and not acc:
+            g.zero_()
+        return g
+
+    if grp.rank == 0:                       # TV is replicated: count its gradient once
+        d_img = torch.empty_like(level_img)
+        ops.tv_bwd(level_img, sums2, tvw, gsc, d_img, False)
+    else:
+        d_img = torch.zeros_like(level_img)
+    g = None
+    masked = False
+    for sidx in range(plan.n_steps_needed - 1, -1, -1):
+        st = plan.steps[sidx]
+        x = sh.bufs[sidx - 1] if sidx > 0 else sh.xin
+        y = sh.bufs[sidx]
+        for k in plan.taps_at.get(sidx, ()):
+            g = tap_grad(k, _interior(y), g)
+        if g is None:
+            continue
+        if st[0] == 'conv':
+            if not masked:
+                ops.relu_bwd_(g, _interior(y))
+            masked = False
+            gpad = _conv_bwd_data_padded(g, x, st[1])
+            if sidx > 0:
+                rows = _rows(gpad)
+                par.halo_exchange_bwd(grp, rows, sh.scratch_rows(rows.shape[1], rows.shape[2]), ops.add_rows)
+                g = _interior(gpad)
+            else:
+                lo, hi = max(band.r0 - 1, 0), min(band.r1 + 1, H)
+                c0 = gpad.shape[1]
+                ops.hwc_to_chw(gpad, d_img, c0, (hi - lo) * W, True, plane=H * W,
+                               x_off=(lo - (band.r0 - 1)) * W * c0, y_off=lo * W)
+                g = None
+        else:
+            xi = _interior(x)
+            gx = torch.empty(xi.shape, dtype=torch.float32, device=dev).contiguous(memory_format=_CL)
+            fuse = sidx > 0 and plan.steps[sidx - 1][0] == 'conv' and (sidx - 1) not in plan.taps_at
+            ops.maxpool2x2_bwd(g, xi, gx, fuse)
+            masked = fuse
+            g = gx
+    return d_img

@@ -34,6 +34,17 @@ class ThreadGroup:
         t.copy_(total)
         sh['barrier'].wait()
 
+    def exchange(self, sends, recvs):
+        """In-process stand-in for the grouped NCCL send/recv: post, barrier, copy, barrier (all threads enqueue on
+        the same stream, so the copies are ordered after the producers' kernels)."""
+        sh = self.shared
+        for t, peer in sends:
+            sh['mail'][(self.rank, peer)] = t
+        sh['barrier'].wait()
+        for t, peer in recvs:
+            t.copy_(sh['mail'][(peer, self.rank)])
+        sh['barrier'].wait()
+
 
 @pytest.fixture(autouse=True)
 def exact_convs():
@@ -93,6 +104,72 @@ def test_sharded_level_matches_unsharded(seeded_vgg, world, precision):
     gsum = sum(results[r][1] for r in range(world))
     gerr = float(torch.linalg.norm(gsum - ref_grad) / torch.linalg.norm(ref_grad))
     assert gerr < (1e-4 if precision == 'fp32' else 2e-3)
+
+
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize('world,H,W', [(2, 128, 96), (4, 128, 64), (4, 256, 48), (8, 256, 32)])
+def test_halo_exchange_level_matches_unsharded(seeded_vgg, world, H, W):
+    """Channels-last path, one halo row exchanged per convolution: nothing is approximated, so the sharded level
+    must reproduce the unsharded one up to summation order (fp32-exact convolutions here)."""
+    from artstyletransfer_b200 import math_utils, neural_style_transfer as nst, parallel
+    from artstyletransfer_b200.sharded_path import ShardedPathLevel
+    content, style = O.synthetic_images(H, W, seed=7)
+    init = np.clip(content * 0.5 + np.random.default_rng(8).uniform(0, 1, size=content.shape) * 0.5, 0, 1).astype(np.float32)
+    net, cidx, sidx = math_utils.prepare_model('vgg19', dev())
+    c_img, s_img = nst.prepare_img(content, dev()), nst.prepare_img(style, dev())
+    lb = nst.LossBuilder(cidx, sidx, c_img, s_img, net, *WEIGHTS)
+    img = nst.prepare_img(init, dev()).requires_grad_(True)
+    total, c, s, tv = lb.build(img)
+    total.backward()
+    ref = [v.item() for v in (total, c, s, tv)]
+    ref_grad = img.grad.clone()
+    plan = lb.path_plan(img)
+    assert plan is not None
+
+    shared = {'bufs': [None] * world, 'barrier': threading.Barrier(world, timeout=60), 'mail': {}}
+    results = [None] * world
+    errors = []
+
+    def run(rank):
+        try:
+            torch.cuda.set_device(dev())
+            grp = ThreadGroup(rank, world, shared)
+            sh = ShardedPathLevel(grp, plan, c_img, s_img, cidx, sidx, WEIGHTS, H, W)
+            out = []
+            # the schedules are called directly: torch runs every autograd backward of a device on ONE engine thread,
+            # so R emulated ranks whose backward passes wait for one another cannot go through .backward() here
+            # (the autograd wrapper itself is exercised by the multi-GPU run, one process per rank)
+            from artstyletransfer_b200.sharded_path import sharded_forward, sharded_backward
+            for _ in range(2):                                  # persistent buffers: a second closure must agree
+                x = nst.prepare_img(init, dev())
+                with torch.no_grad():
+                    out4, state = sharded_forward(sh, x)
+                    grad = sharded_backward(state, None)
+                out.append(([v.item() for v in out4], grad.clone()))
+            assert out[0][0] == out[1][0] and torch.equal(out[0][1], out[1][1])
+            results[rank] = out[0]
+        except Exception as e:   # pragma: no cover
+            import traceback
+            errors.append(traceback.format_exc())
+            shared['barrier'].abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for r in range(world):
+        np.testing.assert_allclose(results[r][0], ref, rtol=1e-4)
+        assert results[r][0] == results[0][0]                 # every rank sees bit-identical losses
+    gsum = sum(results[r][1] for r in range(world))
+    gerr = float(torch.linalg.norm(gsum - ref_grad) / torch.linalg.norm(ref_grad))
+    assert gerr < 5e-4, gerr
+    # each rank's gradient lives in its band rows +- 1 (TV gradient on rank 0 aside)
+    hb = H // world
+    for r in range(1, world):
+        gr = results[r][1]
+        lo, hi = max(r * hb - 1, 0), min((r + 1) * hb + 1, H)
+        assert float(gr[:, :, :lo].abs().max() if lo > 0 else 0.0) == 0.0
+        assert float(gr[:, :, hi:].abs().max() if hi < H else 0.0) == 0.0
 
 
 def test_band_plan_and_pack_layout():

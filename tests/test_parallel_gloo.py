@@ -80,6 +80,81 @@ def test_band_sums_equal_full_grams_over_gloo():
     assert out[0][0] == out[1][0]              # all ranks hold identical reduced values
 
 
+def _halo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import torch.nn.functional as F
+        from artstyletransfer_b200 import parallel
+        torch.set_num_threads(2)
+        parallel.init_sharding()
+        grp = parallel._GROUP
+        H, W, C1, C2 = 24, 10, 4, 6
+        hb = H // world
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn((1, C1, H, W), generator=g, dtype=torch.float64)
+        w1 = torch.randn((C2, C1, 3, 3), generator=g, dtype=torch.float64)
+        w2 = torch.randn((C1, C2, 3, 3), generator=g, dtype=torch.float64)
+        gout = torch.randn((1, C1, H, W), generator=g, dtype=torch.float64)
+        # reference: two stacked 3x3 convolutions on the whole image, gradient of <y, gout> w.r.t. x
+        xr = x.clone().requires_grad_(True)
+        yr = F.conv2d(F.conv2d(xr, w1, padding=1), w2, padding=1)
+        (gref,) = torch.autograd.grad(yr, xr, gout)
+        # sharded: each rank owns hb rows; padded NHWC bands, one halo row exchanged per convolution
+        r0, r1 = rank * hb, (rank + 1) * hb
+
+        def padded(c):
+            return torch.zeros((hb + 2, W, c), dtype=torch.float64)
+
+        def conv_band(pad_rows, wgt):      # (hb+2, W, Cin) -> (hb, W, Cout), zero padding left/right only
+            xin = pad_rows.permute(2, 0, 1)[None]
+            return F.conv2d(xin, wgt, padding=(0, 1))[0].permute(1, 2, 0).contiguous()
+
+        a0 = padded(C1)
+        a0[1:-1] = x[0, :, r0:r1].permute(1, 2, 0)
+        parallel.halo_exchange_fwd(grp, a0)
+        a1 = padded(C2)
+        a1[1:-1] = conv_band(a0, w1)
+        parallel.halo_exchange_fwd(grp, a1)
+        y = conv_band(a1, w2)
+        fwd_err = float((y - yr[0, :, r0:r1].permute(1, 2, 0)).abs().max())
+
+        def conv_band_bwd(gy, wgt, cin):   # adjoint of conv_band: (hb, W, Cout) -> padded (hb+2, W, Cin)
+            xin = torch.zeros((1, cin, hb + 2, W), dtype=torch.float64, requires_grad=True)
+            yy = F.conv2d(xin, wgt, padding=(0, 1))
+            (gx,) = torch.autograd.grad(yy, xin, gy.permute(2, 0, 1)[None])
+            return gx[0].permute(1, 2, 0).contiguous()
+
+        def add_rows(da, sa, db, sb):
+            if da is not None:
+                da += sa
+            if db is not None:
+                db += sb
+
+        g1 = conv_band_bwd(gout[0, :, r0:r1].permute(1, 2, 0).contiguous(), w2, C2)
+        parallel.halo_exchange_bwd(grp, g1, torch.zeros((2, W, C2), dtype=torch.float64), add_rows)
+        g0 = conv_band_bwd(g1[1:-1].contiguous(), w1, C1)
+        parallel.halo_exchange_bwd(grp, g0, torch.zeros((2, W, C1), dtype=torch.float64), add_rows)
+        bwd_err = float((g0[1:-1] - gref[0, :, r0:r1].permute(1, 2, 0)).abs().max())
+        out[rank] = (fwd_err, bwd_err)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_halo_exchange_reproduces_full_convolutions_over_gloo(world):
+    """Host logic of the per-layer halo exchange (parallel.halo_exchange_fwd / _bwd) with real send/recv between
+    processes: two stacked 3x3 convolutions on row bands == the same convolutions on the whole image, forward and
+    backward (fp64, exact up to rounding)."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_halo_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert sorted(out.keys()) == list(range(world))
+    for rank in range(world):
+        fwd_err, bwd_err = out[rank]
+        assert fwd_err < 1e-10 and bwd_err < 1e-10, (rank, fwd_err, bwd_err)
+
+
 def test_init_sharding_requires_a_group():
     from artstyletransfer_b200 import parallel
     parallel.disable_sharding()
