@@ -22,6 +22,7 @@ ReLUs are in place) and relu5_1.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -29,6 +30,11 @@ import torch
 from . import ops
 
 _CL = torch.channels_last
+# cuDNN's fused conv + bias + ReLU (torch.cudnn_convolution_relu) runs at the speed of the bare convolution on B200 and is
+# bit-identical to conv followed by ast_bias_relu_nhwc (tests/tools/conv_fused_probe.py, profiles/r01_conv_fused.jsonl),
+# so the unsharded path lets cuDNN apply the epilogue.  '0' = separate bias/ReLU kernel (what the sharded path uses:
+# its convolutions write straight into padded band buffers through cudnn_convolution.out).
+FUSED_CONV_RELU = os.environ.get('AST_FUSED_CONV_RELU', '1') != '0'
 
 
 class FeaturePlan:
@@ -128,8 +134,13 @@ def features_forward(plan: FeaturePlan, img: torch.Tensor, keep: bool):
     for sidx in range(plan.n_steps_needed):
         st = plan.steps[sidx]
         if st[0] == 'conv':
-            y = _conv_fwd(x, st[1])
-            ops.bias_relu_(y, st[2])
+            if FUSED_CONV_RELU:
+                y = torch.cudnn_convolution_relu(x, st[1], st[2], [1, 1], [1, 1], [1, 1], 1)
+                if not y.is_contiguous(memory_format=_CL):
+                    y = y.contiguous(memory_format=_CL)
+            else:
+                y = _conv_fwd(x, st[1])
+                ops.bias_relu_(y, st[2])
         else:
             y = torch.empty((1, x.shape[1], x.shape[2] // 2, x.shape[3] // 2), dtype=torch.float32, device=x.device,
                             memory_format=_CL)

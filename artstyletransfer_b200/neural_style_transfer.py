@@ -43,6 +43,12 @@ PRECISION = None                # None -> ops.DEFAULT_PRECISION ('tf32'); 'fp32'
 # transposes + this library's glue and (HW, C) Gram kernels).  False: torch modules + autograd around the NCHW
 # kernels (also what 'fp32' precision and non-Vgg19 feature nets use).
 CHANNELS_LAST_PATH = os.environ.get('AST_CHANNELS_LAST', '1') != '0'
+# True: after GRAPH_WARMUP eager closures the whole closure (every level forward + backward, the pyramid
+# resampling, the partial-Gram / halo / image-gradient collectives) is captured ONCE into a CUDA graph and
+# replayed: a closure is ~1 000 launches, and at the small pyramid levels (and on row bands) the host cannot
+# issue them as fast as the GPU retires them.
+GRAPH_CLOSURE = os.environ.get('AST_CUDA_GRAPH', '1') != '0'
+GRAPH_WARMUP = 2
 
 
 class ContentStylePair:
@@ -188,45 +194,92 @@ class _Job:
         self.optimizer_name = optimizer_name
         self.init_img_name = init_img_name
         self.weights = (content_weight, style_weight, tv_weight)
+        self._graph = None            # (CUDAGraph, static total loss, static image gradient) once captured
+        self._graph_failed = False
+        self._eager_closures = 0
+
+    # ---- the closure (:152-202) --------------------------------------------------------------------------
+    def _evaluate(self):
+        """All levels forward, summed loss, backward, image-gradient sync: everything a closure launches."""
+        optimizing_img, loss_builders = self.optimizing_img, self.loss_builders
+        content_weight, style_weight, tv_weight = self.weights
+        optimizing_img_levels = None
+        total_loss = None
+        for i in range(len(loss_builders)):
+            # lower resolutions of optimizing_img: chained bicubic 2x down (:168-176)
+            if i == 0:
+                optimizing_img_levels = [optimizing_img]
+            else:
+                optimizing_img_levels.append(ops.bicubic_half(optimizing_img_levels[i - 1]))
+            total_loss_l, content_loss, style_loss, tv_loss = loss_builders[i].build(optimizing_img_levels[i])
+            if total_loss is None:
+                total_loss = total_loss_l
+            else:
+                previous_loss_importance = 1.0
+                total_loss = previous_loss_importance * total_loss + total_loss_l
+            if VERBOSE:
+                with torch.no_grad():
+                    print(f' - level {i} | level loss={total_loss_l.item():.3e}, '
+                          f'content_loss={content_weight * content_loss.item():.3e}, '
+                          f'style loss={style_weight * style_loss:.3e}, '
+                          f'tv loss={tv_weight * tv_loss.item():.3e}')
+        if total_loss.requires_grad:
+            total_loss.backward()
+        if torch.is_grad_enabled():
+            _parallel.sync_image_grad(optimizing_img)
+        return total_loss
+
+    def _graph_eligible(self):
+        return (GRAPH_CLOSURE and not VERBOSE and not self._graph_failed and torch.is_grad_enabled()
+                and not ops.STATS.enabled and self._eager_closures >= GRAPH_WARMUP)
+
+    def _capture(self):
+        """Capture one closure into a CUDA graph.  The image leaf is updated in place by Adam / LBFGS, so its
+        storage is the graph's static input; the summed loss and the image gradient are its static outputs."""
+        dev = self.optimizing_img.device
+        self.optimizing_img.grad = None          # backward() inside the capture creates .grad in the graph's pool
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            total = self._evaluate()
+        static_total = total.detach()
+        static_grad = self.optimizing_img.grad
+        if static_grad is None:
+            raise RuntimeError('closure capture produced no image gradient')
+        self._graph = (graph, static_total, static_grad)
 
     def closure(self):
         try:
-            optimizer, optimizing_img, loss_builders = self.optimizer, self.optimizing_img, self.loss_builders
-            content_weight, style_weight, tv_weight = self.weights
+            optimizer, optimizing_img = self.optimizer, self.optimizing_img
             # learning rate schedule (:155-159)
             lr = 0
             for g in optimizer.param_groups:
                 g['lr'] *= 0.999
                 lr = g['lr']
-            if torch.is_grad_enabled():
-                optimizer.zero_grad()
             if VERBOSE:
                 print(f"new lr = {lr}")
                 print(f'{self.optimizer_name} | processing image: {self.init_img_name} | iteration: {self.step:03} :')
-            optimizing_img_levels = None
-            total_loss = None
-            for i in range(len(loss_builders)):
-                # lower resolutions of optimizing_img: chained bicubic 2x down (:168-176)
-                if i == 0:
-                    optimizing_img_levels = [optimizing_img]
-                else:
-                    optimizing_img_levels.append(ops.bicubic_half(optimizing_img_levels[i - 1]))
-                total_loss_l, content_loss, style_loss, tv_loss = loss_builders[i].build(optimizing_img_levels[i])
-                if total_loss is None:
-                    total_loss = total_loss_l
-                else:
-                    previous_loss_importance = 1.0
-                    total_loss = previous_loss_importance * total_loss + total_loss_l
-                if VERBOSE:
-                    with torch.no_grad():
-                        print(f' - level {i} | level loss={total_loss_l.item():.3e}, '
-                              f'content_loss={content_weight * content_loss.item():.3e}, '
-                              f'style loss={style_weight * style_loss:.3e}, '
-                              f'tv loss={tv_weight * tv_loss.item():.3e}')
-            if total_loss.requires_grad:
-                total_loss.backward()
-            if torch.is_grad_enabled():
-                _parallel.sync_image_grad(optimizing_img)
+            if self._graph is None and self._graph_eligible():
+                try:
+                    self._capture()
+                except Exception:
+                    # leave capture mode cleanly and keep working eagerly (e.g. a feature net that syncs)
+                    self._graph_failed = True
+                    self._graph = None
+                    optimizing_img.grad = None
+                    if os.environ.get('AST_CUDA_GRAPH_STRICT', '0') == '1':
+                        raise
+                    traceback.print_exc()
+            if self._graph is not None and torch.is_grad_enabled() and not ops.STATS.enabled and not VERBOSE:
+                graph, static_total, static_grad = self._graph
+                graph.replay()
+                optimizing_img.grad = static_grad      # the replay refilled it (assignment, not accumulation)
+                total_loss = static_total
+            else:
+                if torch.is_grad_enabled():
+                    optimizer.zero_grad()
+                total_loss = self._evaluate()
+                self._eager_closures += 1
             if VERBOSE:
                 with torch.no_grad():
                     print(f'{self.optimizer_name} | total loss={total_loss.item():.3e}')
