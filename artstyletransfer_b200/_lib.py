@@ -52,7 +52,6 @@ SIGNATURES = {
     'ast_maxpool2x2_bwd_nhwc': (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     'ast_chw_to_hwc': (_i, [_p, _i, _i64, _i64, _p, _p]),
     'ast_hwc_to_chw': (_i, [_p, _i, _i64, _p, _i64, _i, _p]),
-    'ast_add_rows': (_i, [_p, _p, _p, _p, _i64, _p]),
     'ast_tv_fwd': (_i, [_p, _i, _i, _i, _p, _p, _p, _sz, _p]),
     'ast_tv_bwd': (_i, [_p, _i, _i, _i, _p, _f, _f, _p, _p, _i, _p]),
     'ast_level_combine': (_i, [_p, _i, _p, _p, _f, _f, _f, _p, _p]),

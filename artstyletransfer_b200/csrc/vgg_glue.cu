@@ -175,29 +175,6 @@ __global__ void __launch_bounds__(kGlueThreads) hwc_to_chw_kernel(const float* _
   }
 }
 
-// dst_a += src_a and dst_b += src_b (n floats each, n % 4 == 0; either pair may be absent): folds the two
-// halo-row gradients received from the neighbouring ranks into the band's edge rows in one launch.
-__global__ void __launch_bounds__(kGlueThreads) add_rows_kernel(float4* __restrict__ dst_a,
-                                                               const float4* __restrict__ src_a,
-                                                               float4* __restrict__ dst_b,
-                                                               const float4* __restrict__ src_b, int64_t n4) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    if (dst_a) {
-      float4 d = dst_a[i];
-      const float4 v = ldg_stream(src_a + i);
-      d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w;
-      dst_a[i] = d;
-    }
-    if (dst_b) {
-      float4 d = dst_b[i];
-      const float4 v = ldg_stream(src_b + i);
-      d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w;
-      dst_b[i] = d;
-    }
-  }
-}
-
 }  // namespace ast
 
 using namespace ast;
@@ -263,19 +240,4 @@ extern "C" int ast_hwc_to_chw(const float* x, int C, int64_t HW, float* y, int64
   hwc_to_chw_kernel<<<glue_grid(HW * C), kGlueThreads, 0, (cudaStream_t)stream>>>(x, C, HW, plane_stride, y,
                                                                                  accumulate ? 1 : 0);
   return check_launch("hwc_to_chw");
-}
-
-extern "C" int ast_add_rows(float* dst_a, const float* src_a, float* dst_b, const float* src_b, int64_t n,
-                            void* stream) {
-  AST_REQUIRE((dst_a != nullptr) == (src_a != nullptr) && (dst_b != nullptr) == (src_b != nullptr), AST_ERR_INVALID,
-              "ast_add_rows: dst/src must come in pairs");
-  AST_REQUIRE(n > 0 && n % 4 == 0, AST_ERR_INVALID, "ast_add_rows: n must be a positive multiple of 4 (got %lld)",
-              (long long)n);
-  AST_REQUIRE(al16(dst_a) && al16(src_a) && al16(dst_b) && al16(src_b), AST_ERR_INVALID,
-              "ast_add_rows: pointers must be 16-byte aligned");
-  if (!dst_a && !dst_b) return AST_OK;
-  add_rows_kernel<<<glue_grid(n / 4), kGlueThreads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<float4*>(dst_a), reinterpret_cast<const float4*>(src_a), reinterpret_cast<float4*>(dst_b),
-      reinterpret_cast<const float4*>(src_b), n / 4);
-  return check_launch("add_rows");
 }

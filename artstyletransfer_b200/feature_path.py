@@ -108,14 +108,26 @@ def plan_for(net) -> Optional[FeaturePlan]:
     return plan
 
 
+def _ckey(kind, x, w):
+    return (kind, int(w.shape[1]), int(w.shape[0]), int(x.shape[2]), int(x.shape[3]))
+
+
 def _conv_fwd(x, w):
-    return torch.ops.aten.cudnn_convolution(x, w, [1, 1], [1, 1], [1, 1], 1, False, False,
-                                            torch.backends.cudnn.allow_tf32)
+    with ops.timed(x.device, _ckey('cudnn_conv_fwd', x, w)):
+        return torch.ops.aten.cudnn_convolution(x, w, [1, 1], [1, 1], [1, 1], 1, False, False,
+                                                torch.backends.cudnn.allow_tf32)
+
+
+def _conv_relu_fwd(x, w, b):
+    with ops.timed(x.device, _ckey('cudnn_conv_bias_relu_fwd', x, w)):
+        y = torch.cudnn_convolution_relu(x, w, b, [1, 1], [1, 1], [1, 1], 1)
+    return y if y.is_contiguous(memory_format=_CL) else y.contiguous(memory_format=_CL)
 
 
 def _conv_bwd_data(g, x, w):
-    gi = torch.ops.aten.convolution_backward(g, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
-                                             [True, False, False])[0]
+    with ops.timed(x.device, _ckey('cudnn_conv_dgrad', x, w)):
+        gi = torch.ops.aten.convolution_backward(g, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                                                 [True, False, False])[0]
     return gi if gi.is_contiguous(memory_format=_CL) else gi.contiguous(memory_format=_CL)
 
 
@@ -135,9 +147,7 @@ def features_forward(plan: FeaturePlan, img: torch.Tensor, keep: bool):
         st = plan.steps[sidx]
         if st[0] == 'conv':
             if FUSED_CONV_RELU:
-                y = torch.cudnn_convolution_relu(x, st[1], st[2], [1, 1], [1, 1], [1, 1], 1)
-                if not y.is_contiguous(memory_format=_CL):
-                    y = y.contiguous(memory_format=_CL)
+                y = _conv_relu_fwd(x, st[1], st[2])
             else:
                 y = _conv_fwd(x, st[1])
                 ops.bias_relu_(y, st[2])

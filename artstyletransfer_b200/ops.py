@@ -71,7 +71,7 @@ _KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_mse_fwd_nhwc': 2, 'ast_gra
                      'ast_tv_fwd': 1, 'ast_tv_bwd': 1, 'ast_level_combine': 1, 'ast_bicubic_down2x': 1,
                      'ast_bicubic_down2x_adj': 1, 'ast_bicubic_resize': 1, 'ast_bicubic_resize_adj': 1,
                      'ast_noise_init': 1, 'ast_bias_relu_nhwc': 1, 'ast_relu_bwd': 1, 'ast_maxpool2x2_nhwc': 1,
-                     'ast_maxpool2x2_bwd_nhwc': 1, 'ast_chw_to_hwc': 1, 'ast_hwc_to_chw': 1, 'ast_add_rows': 1}
+                     'ast_maxpool2x2_bwd_nhwc': 1, 'ast_chw_to_hwc': 1, 'ast_hwc_to_chw': 1}
 
 
 def _launch(dev: torch.device, key, name: str, *args) -> None:
@@ -89,6 +89,26 @@ def _launch(dev: torch.device, key, name: str, *args) -> None:
                 STATS.events.append((key, a, b))
                 return
         L.call(name, *args, st.cuda_stream)
+
+
+class timed:
+    """`with ops.timed(dev, key):` — CUDA events around a region that is NOT one of this library's kernels (a cuDNN
+    convolution, a collective) when bench.py's per-kernel pass is on; free otherwise."""
+    __slots__ = ('dev', 'key', 'a')
+
+    def __init__(self, dev: torch.device, key):
+        self.dev, self.key, self.a = dev, key, None
+
+    def __enter__(self):
+        if STATS.enabled and STATS.timing:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.dev))
+
+    def __exit__(self, *exc):
+        if self.a is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record(torch.cuda.current_stream(self.dev))
+            STATS.events.append((self.key, self.a, b))
 
 
 class _on:
@@ -246,16 +266,6 @@ def hwc_to_chw(x: torch.Tensor, y: torch.Tensor, c: int, hw: int, accumulate: bo
                x_off: int = 0, y_off: int = 0) -> None:
     _launch(x.device, ('hwc_to_chw', c, hw), 'ast_hwc_to_chw', x.data_ptr() + 4 * x_off, c, hw,
             y.data_ptr() + 4 * y_off, hw if plane is None else plane, int(accumulate))
-
-
-def add_rows(dst_a: Optional[torch.Tensor], src_a: Optional[torch.Tensor], dst_b: Optional[torch.Tensor],
-             src_b: Optional[torch.Tensor]) -> None:
-    """dst_a += src_a; dst_b += src_b (contiguous rows of equal length; a pair may be None)."""
-    ref = dst_a if dst_a is not None else dst_b
-    if ref is None:
-        return
-    p = lambda t: t.data_ptr() if t is not None else None
-    _launch(ref.device, ('add_rows', ref.numel()), 'ast_add_rows', p(dst_a), p(src_a), p(dst_b), p(src_b), ref.numel())
 
 
 # ------------------------------------------------------------------------------------------------------

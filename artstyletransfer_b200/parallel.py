@@ -87,38 +87,29 @@ class TorchDistGroup:
             work.wait()
 
 
-def halo_exchange_fwd(group, rows: torch.Tensor) -> None:
-    """rows: (h + 2, w, C) contiguous view of a padded activation band (row 0 and row h+1 are the halos).
-    Sends the first / last owned row to the rank above / below and receives their edge rows into the halos.
-    Halos at the image border are left alone (they hold the convolution's zero padding)."""
+def halo_exchange(group, rows: torch.Tensor, zero_border: bool = False) -> None:
+    """rows: (h + 2, w, C) contiguous view of a padded band (row 0 and row h+1 are the halos).  Sends the first /
+    last owned row to the rank above / below and receives their edge rows into the halos.
+
+    Forward (activations, zero_border=False): halos at the image border are left alone — they hold the
+    convolution's zero padding and nothing ever writes them.
+    Backward (gradients w.r.t. a convolution's output, zero_border=True): the same exchange makes every owned row
+    of the following backward-data convolution complete (it needs gradient rows i-1..i+1); there is no gradient
+    row outside the image, so a border halo is zeroed (gradient buffers are recycled, unlike activation bands)."""
     h = rows.shape[0] - 2
     up, dn = group.rank - 1, group.rank + 1
     sends, recvs = [], []
     if up >= 0:
         sends.append((rows[1], up))
         recvs.append((rows[0], up))
+    elif zero_border:
+        rows[0].zero_()
     if dn < group.world:
         sends.append((rows[h], dn))
         recvs.append((rows[h + 1], dn))
+    elif zero_border:
+        rows[h + 1].zero_()
     group.exchange(sends, recvs)
-
-
-def halo_exchange_bwd(group, rows: torch.Tensor, scratch: torch.Tensor, add_rows) -> None:
-    """Adjoint of halo_exchange_fwd on a padded gradient band: the halo rows hold gradient that belongs to the
-    neighbours' edge rows.  Sends them over, receives the neighbours' halo gradients into scratch (2, w, C) and
-    adds them to the first / last owned row with add_rows(dst_a, src_a, dst_b, src_b)."""
-    h = rows.shape[0] - 2
-    up, dn = group.rank - 1, group.rank + 1
-    sends, recvs = [], []
-    if up >= 0:
-        sends.append((rows[0], up))
-        recvs.append((scratch[0], up))
-    if dn < group.world:
-        sends.append((rows[h + 1], dn))
-        recvs.append((scratch[1], dn))
-    group.exchange(sends, recvs)
-    add_rows(rows[1] if up >= 0 else None, scratch[0] if up >= 0 else None,
-             rows[h] if dn < group.world else None, scratch[1] if dn < group.world else None)
 
 
 _GROUP = None     # set by init_sharding(); None -> single-process path
@@ -301,4 +292,6 @@ def sync_image_grad(optimizing_img) -> None:
         return
     if optimizing_img.grad is None:          # every rank must join the collective
         optimizing_img.grad = torch.zeros_like(optimizing_img)
-    _GROUP.all_reduce_sum(optimizing_img.grad)
+    from . import ops
+    with ops.timed(optimizing_img.device, ('allreduce_image_grad', optimizing_img.numel())):
+        _GROUP.all_reduce_sum(optimizing_img.grad)

@@ -2,10 +2,12 @@
 
 Every rank owns hb = H / R image rows of the level (hb a multiple of 16, so the four 2x2 max-pools never straddle
 ranks) and ONLY computes those: before each 3x3 convolution it swaps one activation row with each neighbour
-(parallel.halo_exchange_fwd; rows are contiguous in NHWC, so they go over NVLink in place, no packing), and in the
-backward the gradient that the convolution's backward-data puts into the halo rows goes back to its owner
-(parallel.halo_exchange_bwd).  The first convolution needs no exchange in either direction: every rank holds the
-whole (3-channel) level image, and the per-closure all-reduce of the image gradient sums the halo rows' gradient.
+(parallel.halo_exchange; rows are contiguous in NHWC, so they go over NVLink in place, no packing).  The backward
+uses the SAME exchange on the gradient w.r.t. each convolution's output: with the neighbours' edge gradient rows
+in the halos, an ordinary symmetric-padding backward-data convolution over the padded band yields complete
+gradients for the owned rows (its two halo output rows are incomplete and ignored) — cuDNN's asymmetric-padding
+backward-data, which the mirrored "send halo gradients back" scheme needs, runs 1.5x slower on B200.  The first
+convolution needs no exchange in the forward: every rank holds the whole (3-channel) level image.
 
 Per level and closure: 12 + 12 grouped send/recv steps (<= 0.8 MB each), ONE all-reduce(sum) of the packed raw
 Grams + content SSE (~2.4 MB), then every rank finalises identically.  Activations live in persistent padded
@@ -64,14 +66,7 @@ class ShardedPathLevel:
             else:
                 h, w = h // 2, w // 2
             self.bufs.append(torch.zeros((1, c, h + 2, w), dtype=torch.float32, device=dev).contiguous(memory_format=_CL))
-        self.scratch = {}
         self.generation = 0
-
-    def scratch_rows(self, w: int, c: int) -> torch.Tensor:
-        key = (w, c)
-        if key not in self.scratch:
-            self.scratch[key] = torch.empty((2, w, c), dtype=torch.float32, device=self.xin.device)
-        return self.scratch[key]
 
     def build(self, level_img: torch.Tensor):
         return ShardPathFn.apply(self, level_img)
@@ -82,19 +77,22 @@ def _interior(buf: torch.Tensor) -> torch.Tensor:
 
 
 def _conv_fwd_into(x_pad, w, out):
-    torch.ops.aten.cudnn_convolution.out(x_pad, w, [0, 1], [1, 1], [1, 1], 1, False, False,
-                                         torch.backends.cudnn.allow_tf32, out=out)
+    with ops.timed(x_pad.device, fp._ckey('cudnn_conv_fwd', out, w)):
+        torch.ops.aten.cudnn_convolution.out(x_pad, w, [0, 1], [1, 1], [1, 1], 1, False, False,
+                                             torch.backends.cudnn.allow_tf32, out=out)
 
 
-def _conv_bwd_data_padded(g, x_pad, w):
-    gi = torch.ops.aten.convolution_backward(g, x_pad, w, None, [1, 1], [0, 1], [1, 1], False, [0, 0], 1,
-                                             [True, False, False])[0]
+def _conv_bwd_data_padded(g_pad, x_pad, w):
+    """Backward-data over the whole padded band (h + 2 rows in, h + 2 rows out, symmetric padding)."""
+    with ops.timed(x_pad.device, fp._ckey('cudnn_conv_dgrad', g_pad, w)):
+        gi = torch.ops.aten.convolution_backward(g_pad, x_pad, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                                                 [True, False, False])[0]
     return gi if gi.is_contiguous(memory_format=_CL) else gi.contiguous(memory_format=_CL)
 
 
 class ShardPathFn(torch.autograd.Function):
     """input: the full level image (every rank has it).  outputs as LevelPathFn; the returned image gradient is
-    this rank's contribution (its band rows +- 1, plus the TV gradient on rank 0) — summed by sync_image_grad."""
+    this rank's contribution (its band rows, plus the TV gradient on rank 0) — summed by sync_image_grad."""
 
     @staticmethod
     def forward(ctx, sh: ShardedPathLevel, level_img):
@@ -133,7 +131,8 @@ def sharded_forward(sh: ShardedPathLevel, level_img: torch.Tensor):
         y = sh.bufs[sidx]
         if st[0] == 'conv':
             if sidx > 0:
-                par.halo_exchange_fwd(grp, _rows(x))
+                with ops.timed(dev, ('halo_exchange_fwd', x.shape[1], x.shape[3])):
+                    par.halo_exchange(grp, _rows(x))
             yi = _interior(y)
             _conv_fwd_into(x, st[1], yi)
             ops.bias_relu_(yi, st[2])
@@ -152,7 +151,8 @@ def sharded_forward(sh: ShardedPathLevel, level_img: torch.Tensor):
                               sh.wss.for_gram(j, c, hw_band, dev))
     xc = taps[sh.cidx]
     ops.mse_fwd(xc, sh.target_content_band, 1.0, packed[sh.content_slot], sh.wss.for_reduce('content', dev))
-    grp.all_reduce_sum(packed)
+    with ops.timed(dev, ('allreduce_packed_grams', sh.n_packed)):
+        grp.all_reduce_sum(packed)
     vals = torch.empty(n_style + 2, dtype=torch.float32, device=dev)
     out4 = torch.empty(4, dtype=torch.float32, device=dev)
     ds = {}
@@ -185,10 +185,16 @@ def sharded_backward(state, g_total) -> torch.Tensor:
     n = len(sh.sidx)
     H, W = sh.H, sh.W
 
-    def tap_grad(k, tap, g):
-        acc = g is not None
+    def new_grad_band(like_interior):
+        """Padded gradient band (1, C, h+2, w) for a tensor shaped like an activation band's interior."""
+        _, c, h, w = like_interior.shape
+        return torch.empty((1, c, h + 2, w), dtype=torch.float32, device=dev).contiguous(memory_format=_CL)
+
+    def tap_grad(k, tap, gp):
+        acc = gp is not None
         if not acc:
-            g = torch.empty(tap.shape, dtype=torch.float32, device=dev).contiguous(memory_format=_CL)
+            gp = new_grad_band(tap)
+        g = _interior(gp)
         c, hw_band = tap.shape[1], tap.shape[2] * tap.shape[3]
         wrote = False
         if k in ds:
@@ -200,43 +206,41 @@ def sharded_backward(state, g_total) -> torch.Tensor:
             wrote = True
         if not wrote and not acc:
             g.zero_()
-        return g
+        return gp
 
     if grp.rank == 0:                       # TV is replicated: count its gradient once
         d_img = torch.empty_like(level_img)
         ops.tv_bwd(level_img, sums2, tvw, gsc, d_img, False)
     else:
         d_img = torch.zeros_like(level_img)
-    g = None
+    gp = None                               # padded gradient band w.r.t. the current step's output
     masked = False
     for sidx in range(plan.n_steps_needed - 1, -1, -1):
         st = plan.steps[sidx]
         x = sh.bufs[sidx - 1] if sidx > 0 else sh.xin
         y = sh.bufs[sidx]
         for k in plan.taps_at.get(sidx, ()):
-            g = tap_grad(k, _interior(y), g)
-        if g is None:
+            gp = tap_grad(k, _interior(y), gp)
+        if gp is None:
             continue
         if st[0] == 'conv':
             if not masked:
-                ops.relu_bwd_(g, _interior(y))
+                ops.relu_bwd_(_interior(gp), _interior(y))
             masked = False
-            gpad = _conv_bwd_data_padded(g, x, st[1])
+            with ops.timed(dev, ('halo_exchange_bwd', gp.shape[1], gp.shape[3])):
+                par.halo_exchange(grp, _rows(gp), zero_border=True)
+            gxp = _conv_bwd_data_padded(gp, x, st[1])       # owned rows complete; its halo rows are not used
             if sidx > 0:
-                rows = _rows(gpad)
-                par.halo_exchange_bwd(grp, rows, sh.scratch_rows(rows.shape[1], rows.shape[2]), ops.add_rows)
-                g = _interior(gpad)
+                gp = gxp
             else:
-                lo, hi = max(band.r0 - 1, 0), min(band.r1 + 1, H)
-                c0 = gpad.shape[1]
-                ops.hwc_to_chw(gpad, d_img, c0, (hi - lo) * W, True, plane=H * W,
-                               x_off=(lo - (band.r0 - 1)) * W * c0, y_off=lo * W)
-                g = None
+                c0 = gxp.shape[1]
+                ops.hwc_to_chw(gxp, d_img, c0, sh.hb * W, True, plane=H * W, x_off=W * c0, y_off=band.r0 * W)
+                gp = None
         else:
             xi = _interior(x)
-            gx = torch.empty(xi.shape, dtype=torch.float32, device=dev).contiguous(memory_format=_CL)
+            gxp = new_grad_band(xi)
             fuse = sidx > 0 and plan.steps[sidx - 1][0] == 'conv' and (sidx - 1) not in plan.taps_at
-            ops.maxpool2x2_bwd(g, xi, gx, fuse)
+            ops.maxpool2x2_bwd(_interior(gp), xi, _interior(gxp), fuse)
             masked = fuse
-            g = gx
+            gp = gxp
     return d_img

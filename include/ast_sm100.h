@@ -115,9 +115,7 @@ int ast_mse_bwd(const float* X, const float* T, int64_t n, float scale, const fl
  *                             applies the backward of the ReLU that produced x (x > 0), fusing two torch kernels
  *   ast_chw_to_hwc / ast_hwc_to_chw : (C, HW) planar <-> (HW, C) interleaved for C <= 16 (the image, its gradient);
  *                             plane_stride = elements between channel planes of the planar side (HW when dense,
- *                             H*W of the whole image when converting a band of rows)
- *   ast_add_rows            : dst_a += src_a, dst_b += src_b (n floats each; a pair may be NULL) — folds the halo-row
- *                             gradients received from the neighbouring ranks into a row band's edge rows */
+ *                             H*W of the whole image when converting a band of rows) */
 int ast_bias_relu_nhwc(float* y, const float* bias, int C, int64_t n_pos, void* stream);
 int ast_relu_bwd(float* g, const float* r, int64_t n, void* stream);
 int ast_maxpool2x2_nhwc(const float* x, int C, int H, int W, float* y, void* stream);
@@ -126,8 +124,6 @@ int ast_maxpool2x2_bwd_nhwc(const float* gy, const float* x, int C, int H, int W
 int ast_chw_to_hwc(const float* x, int C, int64_t HW, int64_t plane_stride, float* y, void* stream);
 int ast_hwc_to_chw(const float* x, int C, int64_t HW, float* y, int64_t plane_stride, int accumulate,
                    void* stream);
-int ast_add_rows(float* dst_a, const float* src_a, float* dst_b, const float* src_b, int64_t n,
-                 void* stream);
 
 /* ---- Total variation (math_utils.py:37-41) -------------------------------------------------
  *   sums[0] = sum |y[..., :-1] - y[..., 1:]|,  sums[1] = sum |y[:, :-1, :] - y[:, 1:, :]|

@@ -112,30 +112,28 @@ def _halo_worker(rank, world, port, out):
 
         a0 = padded(C1)
         a0[1:-1] = x[0, :, r0:r1].permute(1, 2, 0)
-        parallel.halo_exchange_fwd(grp, a0)
+        parallel.halo_exchange(grp, a0)
         a1 = padded(C2)
         a1[1:-1] = conv_band(a0, w1)
-        parallel.halo_exchange_fwd(grp, a1)
+        parallel.halo_exchange(grp, a1)
         y = conv_band(a1, w2)
         fwd_err = float((y - yr[0, :, r0:r1].permute(1, 2, 0)).abs().max())
 
-        def conv_band_bwd(gy, wgt, cin):   # adjoint of conv_band: (hb, W, Cout) -> padded (hb+2, W, Cin)
+        def conv_band_bwd(gpad, wgt, cin):
+            """Symmetric-padding backward-data over the whole padded gradient band (hb+2 rows in and out); with the
+            neighbours' edge gradient rows in the halos its owned rows are complete."""
             xin = torch.zeros((1, cin, hb + 2, W), dtype=torch.float64, requires_grad=True)
-            yy = F.conv2d(xin, wgt, padding=(0, 1))
-            (gx,) = torch.autograd.grad(yy, xin, gy.permute(2, 0, 1)[None])
+            yy = F.conv2d(xin, wgt, padding=1)
+            (gx,) = torch.autograd.grad(yy, xin, gpad.permute(2, 0, 1)[None])
             return gx[0].permute(1, 2, 0).contiguous()
 
-        def add_rows(da, sa, db, sb):
-            if da is not None:
-                da += sa
-            if db is not None:
-                db += sb
-
-        g1 = conv_band_bwd(gout[0, :, r0:r1].permute(1, 2, 0).contiguous(), w2, C2)
-        parallel.halo_exchange_bwd(grp, g1, torch.zeros((2, W, C2), dtype=torch.float64), add_rows)
-        g0 = conv_band_bwd(g1[1:-1].contiguous(), w1, C1)
-        parallel.halo_exchange_bwd(grp, g0, torch.zeros((2, W, C1), dtype=torch.float64), add_rows)
-        bwd_err = float((g0[1:-1] - gref[0, :, r0:r1].permute(1, 2, 0)).abs().max())
+        g1 = torch.full((hb + 2, W, C1), float('nan'), dtype=torch.float64)      # recycled buffer: halos are garbage
+        g1[1:-1] = gout[0, :, r0:r1].permute(1, 2, 0)
+        parallel.halo_exchange(grp, g1, zero_border=True)
+        g0 = conv_band_bwd(g1, w2, C2)            # gradient w.r.t. the first convolution's output band (padded)
+        parallel.halo_exchange(grp, g0, zero_border=True)
+        gx = conv_band_bwd(g0, w1, C1)
+        bwd_err = float((gx[1:-1] - gref[0, :, r0:r1].permute(1, 2, 0)).abs().max())
         out[rank] = (fwd_err, bwd_err)
     finally:
         dist.destroy_process_group()
@@ -143,7 +141,7 @@ def _halo_worker(rank, world, port, out):
 
 @pytest.mark.parametrize('world', [2, 3])
 def test_halo_exchange_reproduces_full_convolutions_over_gloo(world):
-    """Host logic of the per-layer halo exchange (parallel.halo_exchange_fwd / _bwd) with real send/recv between
+    """Host logic of the per-layer halo exchange (parallel.halo_exchange, activations and gradients) with real send/recv between
     processes: two stacked 3x3 convolutions on row bands == the same convolutions on the whole image, forward and
     backward (fp64, exact up to rounding)."""
     mgr = mp.Manager()
