@@ -190,6 +190,7 @@ class _Job:
         self.sharded_levels = _parallel.maybe_shard(self.loss_builders, self.optimizing_img, neural_net,
                                                     content_feature_maps_index, style_feature_maps_indices,
                                                     (content_weight, style_weight, tv_weight))
+        self.pyramid = _parallel.lockstep_pyramid(self.loss_builders) if self.sharded_levels else None
         self.step = 0
         self.optimizer_name = optimizer_name
         self.init_img_name = init_img_name
@@ -205,6 +206,10 @@ class _Job:
         content_weight, style_weight, tv_weight = self.weights
         optimizing_img_levels = None
         total_loss = None
+        if self.pyramid is not None and not VERBOSE:
+            # every level is row-band sharded: all levels in lock-step, grouped halo exchanges (sharded_path.py)
+            total_loss = self.pyramid.evaluate(optimizing_img)
+            loss_builders = []
         for i in range(len(loss_builders)):
             # lower resolutions of optimizing_img: chained bicubic 2x down (:168-176)
             if i == 0:

@@ -87,28 +87,32 @@ class TorchDistGroup:
             work.wait()
 
 
-def halo_exchange(group, rows: torch.Tensor, zero_border: bool = False) -> None:
-    """rows: (h + 2, w, C) contiguous view of a padded band (row 0 and row h+1 are the halos).  Sends the first /
-    last owned row to the rank above / below and receives their edge rows into the halos.
+def halo_exchange(group, rows, zero_border: bool = False) -> None:
+    """rows: one (h + 2, w, C) contiguous view of a padded band, or a list of them (row 0 and row h+1 are the
+    halos).  Sends the first / last owned row of every band to the rank above / below and receives their edge rows
+    into the halos, all in ONE grouped exchange.
 
     Forward (activations, zero_border=False): halos at the image border are left alone — they hold the
     convolution's zero padding and nothing ever writes them.
     Backward (gradients w.r.t. a convolution's output, zero_border=True): the same exchange makes every owned row
     of the following backward-data convolution complete (it needs gradient rows i-1..i+1); there is no gradient
     row outside the image, so a border halo is zeroed (gradient buffers are recycled, unlike activation bands)."""
-    h = rows.shape[0] - 2
+    if torch.is_tensor(rows):
+        rows = [rows]
     up, dn = group.rank - 1, group.rank + 1
     sends, recvs = [], []
-    if up >= 0:
-        sends.append((rows[1], up))
-        recvs.append((rows[0], up))
-    elif zero_border:
-        rows[0].zero_()
-    if dn < group.world:
-        sends.append((rows[h], dn))
-        recvs.append((rows[h + 1], dn))
-    elif zero_border:
-        rows[h + 1].zero_()
+    for r in rows:
+        h = r.shape[0] - 2
+        if up >= 0:
+            sends.append((r[1], up))
+            recvs.append((r[0], up))
+        elif zero_border:
+            r[0].zero_()
+        if dn < group.world:
+            sends.append((r[h], dn))
+            recvs.append((r[h + 1], dn))
+        elif zero_border:
+            r[h + 1].zero_()
     group.exchange(sends, recvs)
 
 
@@ -284,6 +288,15 @@ def maybe_shard(loss_builders, optimizing_img, neural_net, content_idx, style_id
         else:
             lb.replicated_rank0_only = _GROUP.rank != 0
     return n
+
+
+def lockstep_pyramid(loss_builders):
+    """ShardedPyramid over the job's levels when every one of them is a halo-exchange level, else None."""
+    from .sharded_path import ShardedPathLevel, ShardedPyramid
+    shards = [getattr(lb, 'shard', None) for lb in loss_builders]
+    if shards and all(isinstance(s, ShardedPathLevel) for s in shards):
+        return ShardedPyramid(shards)
+    return None
 
 
 def sync_image_grad(optimizing_img) -> None:

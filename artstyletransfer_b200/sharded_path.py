@@ -111,86 +111,160 @@ class ShardPathFn(torch.autograd.Function):
 
 def sharded_forward(sh: ShardedPathLevel, level_img: torch.Tensor):
     """Forward schedule of one sharded level.  Returns (out4 = [total, content, style, tv], state for backward)."""
-    dev = ops._require_cuda(level_img)
-    plan, band, grp = sh.plan, sh.band, sh.group
-    cw, sw, tvw = sh.weights
-    level_img = level_img.contiguous()
-    H, W, hb = sh.H, sh.W, sh.hb
-    if tuple(level_img.shape) != (1, plan.steps[0][3], H, W):
-        raise ValueError(f'sharded level expects {(1, plan.steps[0][3], H, W)}; got {tuple(level_img.shape)}')
-    sh.generation += 1
-    # image band + one row above / below straight from the replicated image (rows outside the image stay 0)
-    lo, hi = max(band.r0 - 1, 0), min(band.r1 + 1, H)
-    c0 = level_img.shape[1]
-    ops.chw_to_hwc(level_img, sh.xin, c0, (hi - lo) * W, plane=H * W, x_off=lo * W,
-                   y_off=(lo - (band.r0 - 1)) * W * c0)
-    x = sh.xin
-    taps = [None] * len(plan.tap_step)
-    for sidx in range(plan.n_steps_needed):
-        st = plan.steps[sidx]
-        y = sh.bufs[sidx]
-        if st[0] == 'conv':
-            if sidx > 0:
-                with ops.timed(dev, ('halo_exchange_fwd', x.shape[1], x.shape[3])):
-                    par.halo_exchange(grp, _rows(x))
-            yi = _interior(y)
-            _conv_fwd_into(x, st[1], yi)
-            ops.bias_relu_(yi, st[2])
-        else:
-            ops.maxpool2x2(_interior(x), _interior(y))
-        for k in plan.taps_at.get(sidx, ()):
-            taps[k] = _interior(y)
-        x = y
-    # raw partial Grams + partial content SSE -> one all-reduce -> identical finalize on every rank
-    n_style = len(sh.sidx)
-    packed = torch.zeros(sh.n_packed, dtype=torch.float32, device=dev)
-    for j, k in enumerate(sh.sidx):
-        f = taps[k]
-        c, hw_band = f.shape[1], f.shape[2] * f.shape[3]
-        ops.gram_mse_fwd_nhwc(f, c, hw_band, 1.0, None, packed[sh.offs[j]:sh.offs[j] + c * c], None,
-                              sh.wss.for_gram(j, c, hw_band, dev))
-    xc = taps[sh.cidx]
-    ops.mse_fwd(xc, sh.target_content_band, 1.0, packed[sh.content_slot], sh.wss.for_reduce('content', dev))
-    with ops.timed(dev, ('allreduce_packed_grams', sh.n_packed)):
-        grp.all_reduce_sum(packed)
-    vals = torch.empty(n_style + 2, dtype=torch.float32, device=dev)
-    out4 = torch.empty(4, dtype=torch.float32, device=dev)
-    ds = {}
-    for j, k in enumerate(sh.sidx):
-        c = sh.channels[j]
-        st_ = par.LAYER_STRIDE[k]
-        hw_global = (H // st_) * (W // st_)
-        d = torch.empty((c, c), dtype=torch.float32, device=dev)
-        ops.gram_finalize(packed[sh.offs[j]:sh.offs[j] + c * c], c, 1.0 / (c * hw_global), sh.target_grams[j], d,
-                          vals[j], sh.fin_ws[j])
-        ds[k] = (d, hw_global)
-    torch.mul(packed[sh.content_slot], 1.0 / sh.content_numel_global, out=vals[n_style])
-    sums2 = torch.empty(2, dtype=torch.float32, device=dev)
-    ops.tv_fwd(level_img, sums2, vals[n_style + 1], sh.wss.for_reduce('tv', dev))
-    ops._launch(dev, ('combine',), 'ast_level_combine', vals.data_ptr(), n_style, vals[n_style].data_ptr(),
-                vals[n_style + 1].data_ptr(), cw, sw, tvw, out4.data_ptr())
-    return out4, (sh, sh.generation, ds, level_img, sums2)
+    out4s, state = pyramid_forward([sh], [level_img])
+    return out4s[0], state
 
 
 def sharded_backward(state, g_total) -> torch.Tensor:
     """Backward schedule: this rank's contribution to the level image's gradient (g_total: upstream scalar or None)."""
-    sh, generation, ds, level_img, sums2 = state
-    if generation != sh.generation:
-        raise RuntimeError('sharded level: backward() after a newer forward() of the same level — its activation '
-                           'bands are persistent buffers; run forward and backward of a closure back to back')
-    plan, band, grp = sh.plan, sh.band, sh.group
-    cw, sw, tvw = sh.weights
-    dev = level_img.device
+    return pyramid_backward(state, g_total)[0]
+
+
+class ShardedPyramid:
+    """All sharded levels of a job evaluated in LOCK-STEP: the pyramid levels' feature paths do not depend on one
+    another, so step s of every level runs before step s+1 of any, and the halo rows of all levels travel in ONE
+    grouped send/recv per step (13 + 13 per closure instead of 13 + 13 per level), the raw Grams of all levels in
+    ONE all-reduce.  A send/recv group costs ~30 us of latency on NVLink whatever it carries (rows are <= 0.8 MB)."""
+
+    def __init__(self, levels: List[ShardedPathLevel]):
+        self.levels = list(levels)
+
+    def evaluate(self, optimizing_img: torch.Tensor):
+        """image leaf -> summed loss over the levels (neural_style_transfer.py:168-185), differentiable."""
+        return PyramidFn.apply(self, optimizing_img)
+
+
+class PyramidFn(torch.autograd.Function):
+    """image -> total loss of the whole pyramid: chained bicubic 2x down (:168-176), every level's loss in
+    lock-step, plain sum in level order (:180-185, previous_loss_importance = 1); backward adds the bicubic
+    adjoint chain.  Per-level (total, content, style, tv) are kept in `last_out4` for verbose printing."""
+
+    @staticmethod
+    def forward(ctx, pyr: ShardedPyramid, img):
+        ops._require_cuda(img)
+        imgs = [img.contiguous()]
+        for i in range(1, len(pyr.levels)):
+            imgs.append(ops.bicubic_down_raw(imgs[-1], imgs[-1].shape[-2] // 2, imgs[-1].shape[-1] // 2))
+        out4s, state = pyramid_forward(pyr.levels, imgs)
+        total = out4s[0][0]
+        for o in out4s[1:]:
+            total = 1.0 * total + o[0]
+        pyr.last_out4 = out4s
+        if ctx.needs_input_grad[1]:
+            ctx.state = state
+            ctx.shapes = [tuple(t.shape[-2:]) for t in imgs]
+        return total
+
+    @staticmethod
+    def backward(ctx, g_total):
+        state, ctx.state = ctx.state, None
+        d_imgs = pyramid_backward(state, g_total)
+        for i in range(len(d_imgs) - 1, 0, -1):          # adjoint of the down-sampling chain, coarse -> fine
+            ops.bicubic_down_adj_raw(d_imgs[i], *ctx.shapes[i - 1], gx=d_imgs[i - 1], accumulate=True)
+        return None, d_imgs[0]
+
+
+def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Tensor]):
+    """Forward schedule of several sharded levels in lock-step (one level = the plain sharded level).
+    Returns ([out4 per level], state for pyramid_backward)."""
+    dev = ops._require_cuda(*imgs)
+    sh0 = levels[0]
+    plan, grp = sh0.plan, sh0.group
+    imgs = [t.contiguous() for t in imgs]
+    for sh, im in zip(levels, imgs):
+        if sh.plan is not plan or sh.group is not grp:
+            raise ValueError('lock-step levels must share the feature plan and the process group')
+        if tuple(im.shape) != (1, plan.steps[0][3], sh.H, sh.W):
+            raise ValueError(f'sharded level expects {(1, plan.steps[0][3], sh.H, sh.W)}; got {tuple(im.shape)}')
+        sh.generation += 1
+        # image band + one row above / below straight from the replicated image (rows outside the image stay 0)
+        lo, hi = max(sh.band.r0 - 1, 0), min(sh.band.r1 + 1, sh.H)
+        c0 = im.shape[1]
+        ops.chw_to_hwc(im, sh.xin, c0, (hi - lo) * sh.W, plane=sh.H * sh.W, x_off=lo * sh.W,
+                       y_off=(lo - (sh.band.r0 - 1)) * sh.W * c0)
+    xs = [sh.xin for sh in levels]
+    taps = [[None] * len(plan.tap_step) for _ in levels]
+    for sidx in range(plan.n_steps_needed):
+        st = plan.steps[sidx]
+        if st[0] == 'conv' and sidx > 0:
+            with ops.timed(dev, ('halo_exchange_fwd', len(levels), sidx)):
+                par.halo_exchange(grp, [_rows(x) for x in xs])
+        for li, sh in enumerate(levels):
+            x, y = xs[li], sh.bufs[sidx]
+            if st[0] == 'conv':
+                yi = _interior(y)
+                _conv_fwd_into(x, st[1], yi)
+                ops.bias_relu_(yi, st[2])
+            else:
+                ops.maxpool2x2(_interior(x), _interior(y))
+            for k in plan.taps_at.get(sidx, ()):
+                taps[li][k] = _interior(y)
+            xs[li] = y
+    # raw partial Grams + partial content SSE of every level -> ONE all-reduce -> identical finalize on every rank
+    n_packed = sum((sh.n_packed + 3) // 4 * 4 for sh in levels)      # every level's block stays 16-byte aligned
+    packed_all = torch.zeros(n_packed, dtype=torch.float32, device=dev)
+    packs, o = [], 0
+    for li, sh in enumerate(levels):
+        packed = packed_all[o:o + sh.n_packed]
+        o += (sh.n_packed + 3) // 4 * 4
+        packs.append(packed)
+        for j, k in enumerate(sh.sidx):
+            f = taps[li][k]
+            c, hw_band = f.shape[1], f.shape[2] * f.shape[3]
+            ops.gram_mse_fwd_nhwc(f, c, hw_band, 1.0, None, packed[sh.offs[j]:sh.offs[j] + c * c], None,
+                                  sh.wss.for_gram(j, c, hw_band, dev))
+        ops.mse_fwd(taps[li][sh.cidx], sh.target_content_band, 1.0, packed[sh.content_slot],
+                    sh.wss.for_reduce('content', dev))
+    with ops.timed(dev, ('allreduce_packed_grams', n_packed)):
+        grp.all_reduce_sum(packed_all)
+    out4s, per_level = [], []
+    for li, sh in enumerate(levels):
+        packed, im = packs[li], imgs[li]
+        cw, sw, tvw = sh.weights
+        n_style = len(sh.sidx)
+        vals = torch.empty(n_style + 2, dtype=torch.float32, device=dev)
+        out4 = torch.empty(4, dtype=torch.float32, device=dev)
+        ds = {}
+        for j, k in enumerate(sh.sidx):
+            c = sh.channels[j]
+            st_ = par.LAYER_STRIDE[k]
+            hw_global = (sh.H // st_) * (sh.W // st_)
+            d = torch.empty((c, c), dtype=torch.float32, device=dev)
+            ops.gram_finalize(packed[sh.offs[j]:sh.offs[j] + c * c], c, 1.0 / (c * hw_global), sh.target_grams[j], d,
+                              vals[j], sh.fin_ws[j])
+            ds[k] = (d, hw_global)
+        torch.mul(packed[sh.content_slot], 1.0 / sh.content_numel_global, out=vals[n_style])
+        sums2 = torch.empty(2, dtype=torch.float32, device=dev)
+        ops.tv_fwd(im, sums2, vals[n_style + 1], sh.wss.for_reduce('tv', dev))
+        ops._launch(dev, ('combine',), 'ast_level_combine', vals.data_ptr(), n_style, vals[n_style].data_ptr(),
+                    vals[n_style + 1].data_ptr(), cw, sw, tvw, out4.data_ptr())
+        out4s.append(out4)
+        per_level.append((sh, sh.generation, ds, im, sums2))
+    return out4s, per_level
+
+
+def pyramid_backward(state, g_total) -> List[torch.Tensor]:
+    """Backward schedule in lock-step: this rank's contribution to every level image's gradient (its band rows,
+    plus the TV gradient on rank 0).  g_total: upstream scalar gradient (device tensor) or None."""
+    levels = [st[0] for st in state]
+    sh0 = levels[0]
+    plan, grp = sh0.plan, sh0.group
+    dev = state[0][3].device
     gsc = ops._gscale(g_total, dev)
-    n = len(sh.sidx)
-    H, W = sh.H, sh.W
+    for sh, generation, *_ in state:
+        if generation != sh.generation:
+            raise RuntimeError('sharded level: backward() after a newer forward() of the same level — its activation '
+                               'bands are persistent buffers; run forward and backward of a closure back to back')
 
     def new_grad_band(like_interior):
         """Padded gradient band (1, C, h+2, w) for a tensor shaped like an activation band's interior."""
         _, c, h, w = like_interior.shape
         return torch.empty((1, c, h + 2, w), dtype=torch.float32, device=dev).contiguous(memory_format=_CL)
 
-    def tap_grad(k, tap, gp):
+    def tap_grad(li, k, tap, gp):
+        sh, _, ds, _, _ = state[li]
+        cw, sw, tvw = sh.weights
+        n = len(sh.sidx)
         acc = gp is not None
         if not acc:
             gp = new_grad_band(tap)
@@ -208,39 +282,49 @@ def sharded_backward(state, g_total) -> torch.Tensor:
             g.zero_()
         return gp
 
-    if grp.rank == 0:                       # TV is replicated: count its gradient once
-        d_img = torch.empty_like(level_img)
-        ops.tv_bwd(level_img, sums2, tvw, gsc, d_img, False)
-    else:
-        d_img = torch.zeros_like(level_img)
-    gp = None                               # padded gradient band w.r.t. the current step's output
-    masked = False
+    d_imgs = []
+    for sh, _, _, im, sums2 in state:
+        if grp.rank == 0:                       # TV is replicated: count its gradient once
+            d = torch.empty_like(im)
+            ops.tv_bwd(im, sums2, sh.weights[2], gsc, d, False)
+        else:
+            d = torch.zeros_like(im)
+        d_imgs.append(d)
+    gps = [None] * len(levels)                  # padded gradient band w.r.t. the current step's output, per level
+    masked = [False] * len(levels)
     for sidx in range(plan.n_steps_needed - 1, -1, -1):
         st = plan.steps[sidx]
-        x = sh.bufs[sidx - 1] if sidx > 0 else sh.xin
-        y = sh.bufs[sidx]
-        for k in plan.taps_at.get(sidx, ()):
-            gp = tap_grad(k, _interior(y), gp)
-        if gp is None:
+        for li, sh in enumerate(levels):
+            for k in plan.taps_at.get(sidx, ()):
+                gps[li] = tap_grad(li, k, _interior(sh.bufs[sidx]), gps[li])
+        live = [li for li in range(len(levels)) if gps[li] is not None]
+        if not live:
             continue
         if st[0] == 'conv':
-            if not masked:
-                ops.relu_bwd_(_interior(gp), _interior(y))
-            masked = False
-            with ops.timed(dev, ('halo_exchange_bwd', gp.shape[1], gp.shape[3])):
-                par.halo_exchange(grp, _rows(gp), zero_border=True)
-            gxp = _conv_bwd_data_padded(gp, x, st[1])       # owned rows complete; its halo rows are not used
-            if sidx > 0:
-                gp = gxp
-            else:
-                c0 = gxp.shape[1]
-                ops.hwc_to_chw(gxp, d_img, c0, sh.hb * W, True, plane=H * W, x_off=W * c0, y_off=band.r0 * W)
-                gp = None
+            for li in live:
+                if not masked[li]:
+                    ops.relu_bwd_(_interior(gps[li]), _interior(levels[li].bufs[sidx]))
+                masked[li] = False
+            with ops.timed(dev, ('halo_exchange_bwd', len(live), sidx)):
+                par.halo_exchange(grp, [_rows(gps[li]) for li in live], zero_border=True)
+            for li in live:
+                sh = levels[li]
+                x = sh.bufs[sidx - 1] if sidx > 0 else sh.xin
+                gxp = _conv_bwd_data_padded(gps[li], x, st[1])   # owned rows complete; its halo rows are not used
+                if sidx > 0:
+                    gps[li] = gxp
+                else:
+                    c0 = gxp.shape[1]
+                    ops.hwc_to_chw(gxp, d_imgs[li], c0, sh.hb * sh.W, True, plane=sh.H * sh.W, x_off=sh.W * c0,
+                                   y_off=sh.band.r0 * sh.W)
+                    gps[li] = None
         else:
-            xi = _interior(x)
-            gxp = new_grad_band(xi)
             fuse = sidx > 0 and plan.steps[sidx - 1][0] == 'conv' and (sidx - 1) not in plan.taps_at
-            ops.maxpool2x2_bwd(_interior(gp), xi, _interior(gxp), fuse)
-            masked = fuse
-            gp = gxp
-    return d_img
+            for li in live:
+                sh = levels[li]
+                xi = _interior(sh.bufs[sidx - 1] if sidx > 0 else sh.xin)
+                gxp = new_grad_band(xi)
+                ops.maxpool2x2_bwd(_interior(gps[li]), xi, _interior(gxp), fuse)
+                masked[li] = fuse
+                gps[li] = gxp
+    return d_imgs

@@ -38,11 +38,14 @@ class ThreadGroup:
         """In-process stand-in for the grouped NCCL send/recv: post, barrier, copy, barrier (all threads enqueue on
         the same stream, so the copies are ordered after the producers' kernels)."""
         sh = self.shared
-        for t, peer in sends:
-            sh['mail'][(self.rank, peer)] = t
+        for peer in {p for _, p in sends}:
+            sh['mail'][(self.rank, peer)] = [t for t, p in sends if p == peer]     # matched in issue order, like NCCL
         sh['barrier'].wait()
+        taken = {}
         for t, peer in recvs:
-            t.copy_(sh['mail'][(peer, self.rank)])
+            i = taken.get(peer, 0)
+            t.copy_(sh['mail'][(peer, self.rank)][i])
+            taken[peer] = i + 1
         sh['barrier'].wait()
 
 
@@ -170,6 +173,67 @@ def test_halo_exchange_level_matches_unsharded(seeded_vgg, world, H, W):
         lo, hi = max(r * hb - 1, 0), min((r + 1) * hb + 1, H)
         assert float(gr[:, :, :lo].abs().max() if lo > 0 else 0.0) == 0.0
         assert float(gr[:, :, hi:].abs().max() if hi < H else 0.0) == 0.0
+
+
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize('world', [2, 4])
+def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, world):
+    """Two pyramid levels evaluated in lock-step with grouped halo exchanges == the unsharded closure
+    (bicubic chain + both levels + backward), summed over the emulated ranks."""
+    from artstyletransfer_b200 import math_utils, neural_style_transfer as nst, ops
+    from artstyletransfer_b200.sharded_path import PyramidFn, ShardedPathLevel, ShardedPyramid
+    H, W = 256, 96
+    content, style = O.synthetic_images(H, W, seed=11)
+    init = np.clip(content * 0.5 + np.random.default_rng(12).uniform(0, 1, size=content.shape) * 0.5, 0, 1).astype(np.float32)
+    net, cidx, sidx = math_utils.prepare_model('vgg19', dev())
+    c_lv = [content, content[::2, ::2].copy()]
+    s_lv = [style, style[::2, ::2].copy()]
+    c_img = [nst.prepare_img(c, dev()) for c in c_lv]
+    s_img = [nst.prepare_img(s_, dev()) for s_ in s_lv]
+    lbs = [nst.LossBuilder(cidx, sidx, c, s_, net, *WEIGHTS) for c, s_ in zip(c_img, s_img)]
+    img = nst.prepare_img(init, dev()).requires_grad_(True)
+    lv1 = ops.bicubic_half(img)
+    t0 = lbs[0].build(img)[0]
+    t1 = lbs[1].build(lv1)[0]
+    total = 1.0 * t0 + t1
+    total.backward()
+    ref_total, ref_grad = total.item(), img.grad.clone()
+    plan = lbs[0].path_plan(img)
+
+    shared = {'bufs': [None] * world, 'barrier': threading.Barrier(world, timeout=60), 'mail': {}}
+    results = [None] * world
+    errors = []
+
+    class Ctx:
+        needs_input_grad = (False, True)
+
+    def run(rank):
+        try:
+            torch.cuda.set_device(dev())
+            grp = ThreadGroup(rank, world, shared)
+            levels = [ShardedPathLevel(grp, plan, c_img[i], s_img[i], cidx, sidx, WEIGHTS, H >> i, W >> i) for i in range(2)]
+            pyr = ShardedPyramid(levels)
+            x = nst.prepare_img(init, dev())
+            ctx = Ctx()
+            with torch.no_grad():
+                t = PyramidFn.forward(ctx, pyr, x)
+                _, g = PyramidFn.backward(ctx, None)
+            results[rank] = (t.item(), g.clone())
+        except Exception:   # pragma: no cover
+            import traceback
+            errors.append(traceback.format_exc())
+            shared['barrier'].abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for r in range(world):
+        assert abs(results[r][0] - ref_total) <= 1e-4 * abs(ref_total)
+        assert results[r][0] == results[0][0]
+    gsum = sum(results[r][1] for r in range(world))
+    gerr = float(torch.linalg.norm(gsum - ref_grad) / torch.linalg.norm(ref_grad))
+    assert gerr < 5e-4, gerr
 
 
 def test_band_plan_and_pack_layout():
