@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libast_sm100.so')
 
-AST_ABI_VERSION = 1
+AST_ABI_VERSION = 2
 AST_PREC_TF32, AST_PREC_FP32 = 0, 1
 AST_LAYOUT_CHW, AST_LAYOUT_HWC = 0, 1
 AST_COORD_TORCH, AST_COORD_CV2 = 0, 1
@@ -39,10 +39,10 @@ SIGNATURES = {
     'ast_gram_workspace_bytes': (_sz, [_i, _i64]),
     'ast_gram_tf32_supported': (_i, [_p, _i, _i64, _i64]),
     'ast_gram_mse_fwd': (_i, [_p, _i, _i64, _i64, _f, _p, _p, _p, _p, _sz, _i, _p]),
-    'ast_gram_finalize': (_i, [_p, _i, _f, _p, _p, _p, _p, _sz, _p]),
+    'ast_gram_finalize': (_i, [_p, _i, _f, _p, _p, _p, _p, _sz, _i, _p]),
     'ast_gram_bwd': (_i, [_p, _p, _i, _i64, _i64, _f, _p, _p, _i, _i, _p]),
-    'ast_gram_mse_fwd_nhwc': (_i, [_p, _i, _i64, _f, _p, _p, _p, _p, _sz, _p]),
-    'ast_gram_bwd_nhwc': (_i, [_p, _p, _i, _i64, _f, _p, _p, _i, _p]),
+    'ast_gram_mse_fwd_nhwc': (_i, [_p, _i, _i64, _f, _p, _p, _p, _p, _sz, _i, _p]),
+    'ast_gram_bwd_nhwc': (_i, [_p, _p, _i, _i64, _f, _p, _p, _i, _i, _p]),
     'ast_reduce_workspace_bytes': (_sz, []),
     'ast_mse_fwd': (_i, [_p, _p, _i64, _f, _p, _p, _sz, _p]),
     'ast_mse_bwd': (_i, [_p, _p, _i64, _f, _p, _p, _i, _p]),

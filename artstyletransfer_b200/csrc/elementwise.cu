@@ -95,22 +95,23 @@ __global__ void __launch_bounds__(kThreads) tv_fwd_kernel(const float* __restric
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const int64_t rows = (int64_t)C * H;
   if (vec_ok) {
+    // one image row per block iteration, threads stride along the row: no per-element 64-bit divisions
     const int w4 = W >> 2;
-    const int64_t n4 = rows * w4;
     int iter = 0;
-    for (int64_t i = tid; i < n4; i += nthreads) {
-      const int64_t row = i / w4;
-      const int xq = (int)(i - row * w4);
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
       const int y = (int)(row % H);
-      const float* p = Y + row * W + (xq << 2);
-      const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-      sx += fabsf(a.x - a.y) + fabsf(a.y - a.z) + fabsf(a.z - a.w);
-      if (xq + 1 < w4) sx += fabsf(a.w - __ldg(p + 4));
-      if (y + 1 < H) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p + W));
-        sy += fabsf(a.x - b.x) + fabsf(a.y - b.y) + fabsf(a.z - b.z) + fabsf(a.w - b.w);
+      const float* r = Y + row * W;
+      for (int xq = threadIdx.x; xq < w4; xq += blockDim.x) {
+        const float* p = r + (xq << 2);
+        const float4 a = ldg_stream(reinterpret_cast<const float4*>(p));
+        sx += fabsf(a.x - a.y) + fabsf(a.y - a.z) + fabsf(a.z - a.w);
+        if (xq + 1 < w4) sx += fabsf(a.w - __ldg(p + 4));
+        if (y + 1 < H) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p + W));
+          sy += fabsf(a.x - b.x) + fabsf(a.y - b.y) + fabsf(a.z - b.z) + fabsf(a.w - b.w);
+        }
+        if ((++iter & 31) == 0) { sxd += sx; syd += sy; sx = sy = 0.f; }
       }
-      if ((++iter & 31) == 0) { sxd += sx; syd += sy; sx = sy = 0.f; }
     }
   } else {
     const int64_t n = rows * W;
@@ -152,11 +153,10 @@ __global__ void __launch_bounds__(kThreads) tv_bwd_kernel(const float* __restric
   if (vec_ok) {
     // 4 consecutive pixels of a row per thread: 16-byte loads of the row, the row above and the row below
     const int w4 = W >> 2;
-    const int64_t n4 = (int64_t)C * H * w4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += nthreads) {
-      const int64_t row = i / w4;
-      const int xq = (int)(i - row * w4);
-      const int y = (int)(row % H);
+    const int64_t rows = (int64_t)C * H;
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+     const int y = (int)(row % H);
+     for (int xq = threadIdx.x; xq < w4; xq += blockDim.x) {
       const float* p = Y + row * W + (xq << 2);
       const float4 a = __ldg(reinterpret_cast<const float4*>(p));
       const float v[6] = {xq > 0 ? __ldg(p - 1) : 0.f, a.x, a.y, a.z, a.w, xq + 1 < w4 ? __ldg(p + 4) : 0.f};
@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(kThreads) tv_bwd_kernel(const float* __restric
         r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
       }
       *o = r;
+     }
     }
     return;
   }

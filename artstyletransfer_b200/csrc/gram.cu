@@ -163,7 +163,14 @@ struct FinalizeArgs {
   float scale;
   int symmetric_src;   // 1: partials hold only bi<=bj tiles (mirror them); 0: single full tile
   int lanes;           // partial lanes per element group (4, 8, 16)
+  int round_out;       // 1: store `out` rounded to nearest TF32 (it only feeds the backward's tensor-core operand)
 };
+
+__device__ __forceinline__ float tf32_rn(float x) {
+  // same rounding as the Gram kernels' operand converter (gram_tc.cu: half an ulp added to the magnitude)
+  const uint32_t u = __float_as_uint(x);
+  return ((u & 0x7f800000u) == 0x7f800000u) ? x : __uint_as_float((u + 0x1000u) & 0xffffe000u);
+}
 
 __global__ void __launch_bounds__(256) gram_finalize_kernel(const __grid_constant__ FinalizeArgs a, ReduceWs* ws) {
   __shared__ float4 lanes[256];
@@ -203,14 +210,16 @@ __global__ void __launch_bounds__(256) gram_finalize_kernel(const __grid_constan
     } else {
       d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
     }
-    *reinterpret_cast<float4*>(a.out + o) = make_float4(d[0], d[1], d[2], d[3]);
+    *reinterpret_cast<float4*>(a.out + o) = a.round_out
+                                                ? make_float4(tf32_rn(d[0]), tf32_rn(d[1]), tf32_rn(d[2]), tf32_rn(d[3]))
+                                                : make_float4(d[0], d[1], d[2], d[3]);
     sq = (double)d[0] * d[0] + (double)d[1] * d[1] + (double)d[2] * d[2] + (double)d[3] * d[3];
     if (a.symmetric_src && pl.tile_bi[t] != pl.tile_bj[t]) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const size_t om = (size_t)(gj + k) * C + gi;
         const float dm = a.A ? v[k] - __ldg(a.A + om) : v[k];
-        a.out[om] = dm;
+        a.out[om] = a.round_out ? tf32_rn(dm) : dm;
         sq += (double)dm * dm;
       }
     }
@@ -223,7 +232,8 @@ __global__ void __launch_bounds__(256) gram_finalize_kernel(const __grid_constan
 }
 
 static int launch_finalize(const GramPlan& plan, const float* partials, int symmetric_src, float scale,
-                           const float* A, float* out, float* loss, void* ws, cudaStream_t stream) {
+                           const float* A, float* out, float* loss, void* ws, cudaStream_t stream,
+                           int round_out = 0) {
   FinalizeArgs fa;
   fa.plan = plan;
   fa.partials = partials;
@@ -232,6 +242,7 @@ static int launch_finalize(const GramPlan& plan, const float* partials, int symm
   fa.loss = loss;
   fa.scale = scale;
   fa.symmetric_src = symmetric_src;
+  fa.round_out = round_out;
   const int elems = plan.n_tiles * plan.TR * plan.TR;
   fa.lanes = (elems <= 4096) ? 16 : (elems <= 16384 ? 8 : 4);
   if (plan.total_parts < 2 * fa.lanes) fa.lanes = 4;
@@ -328,7 +339,7 @@ extern "C" int ast_gram_mse_fwd(const float* F, int C, int64_t HW, int64_t ld, f
 }
 
 extern "C" int ast_gram_mse_fwd_nhwc(const float* F, int C, int64_t HW, float scale, const float* A, float* out,
-                                     float* loss, void* ws, size_t ws_bytes, void* stream_) {
+                                     float* loss, void* ws, size_t ws_bytes, int round_out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   AST_REQUIRE(F && out && ws, AST_ERR_INVALID, "ast_gram_mse_fwd_nhwc: null pointer");
   AST_REQUIRE(HW > 0 && HW <= (int64_t)0x7fffff00, AST_ERR_INVALID, "ast_gram_mse_fwd_nhwc: bad HW=%lld", (long long)HW);
@@ -344,22 +355,22 @@ extern "C" int ast_gram_mse_fwd_nhwc(const float* F, int C, int64_t HW, float sc
   gram_tc_plan(C, HW, sms < 148 ? sms : 148, &plan);
   int rc = gram_tc_fwd(F, C, HW, C, 1, partials, plan, sms, stream);
   if (rc != AST_OK) return rc;
-  return launch_finalize(plan, partials, 1, scale, A, out, loss, ws, stream);
+  return launch_finalize(plan, partials, 1, scale, A, out, loss, ws, stream, round_out ? 1 : 0);
 }
 
 extern "C" int ast_gram_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale,
-                                 float* dF, int accumulate, void* stream_) {
+                                 float* dF, int accumulate, int d_prerounded, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   AST_REQUIRE(D && F && dF, AST_ERR_INVALID, "ast_gram_bwd_nhwc: null pointer");
   AST_REQUIRE(HW > 0 && HW <= (int64_t)0x7fffff00, AST_ERR_INVALID, "ast_gram_bwd_nhwc: bad HW=%lld", (long long)HW);
   AST_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, AST_ERR_UNSUPPORTED,
               "ast_gram_bwd_nhwc: C must be 64, 128, 256 or 512 (got %d)", C);
   AST_REQUIRE(is16(F) && is16(D) && is16(dF), AST_ERR_INVALID, "ast_gram_bwd_nhwc: D/F/dF must be 16-byte aligned");
-  return gram_tc_bwd_nhwc(D, F, C, HW, scale, gscale, dF, accumulate, cached_num_sms(), stream);
+  return gram_tc_bwd_nhwc(D, F, C, HW, scale, gscale, dF, accumulate, d_prerounded ? 1 : 0, cached_num_sms(), stream);
 }
 
 extern "C" int ast_gram_finalize(const float* G_raw, int C, float scale, const float* A, float* out, float* loss,
-                                 void* ws, size_t ws_bytes, void* stream) {
+                                 void* ws, size_t ws_bytes, int round_out, void* stream) {
   AST_REQUIRE(G_raw && out && ws, AST_ERR_INVALID, "ast_gram_finalize: null pointer");
   AST_REQUIRE(C > 0 && C % 16 == 0, AST_ERR_UNSUPPORTED, "ast_gram_finalize: C must be a multiple of 16 (got %d)", C);
   AST_REQUIRE(is16(G_raw) && is16(out) && (!A || is16(A)), AST_ERR_INVALID, "ast_gram_finalize: pointers must be 16-byte aligned");
@@ -368,7 +379,7 @@ extern "C" int ast_gram_finalize(const float* G_raw, int C, float scale, const f
   plan.C = C; plan.TR = C; plan.n_tiles = 1;
   plan.tile_bi[0] = plan.tile_bj[0] = 0;
   plan.part_off[0] = 0; plan.part_cnt[0] = 1; plan.total_parts = 1;
-  return launch_finalize(plan, G_raw, 0, scale, A, out, loss, ws, (cudaStream_t)stream);
+  return launch_finalize(plan, G_raw, 0, scale, A, out, loss, ws, (cudaStream_t)stream, round_out ? 1 : 0);
 }
 
 extern "C" int ast_gram_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, float scale,

@@ -106,30 +106,31 @@ static int make_tmap_nhwc_strips(CUtensorMap* m, const float* base, int C, uint6
 __device__ __forceinline__ uint32_t tf32_half_ulp(uint32_t u) {
   return ((u & 0x7f800000u) == 0x7f800000u) ? u : u + 0x1000u;
 }
+template <int NT = 128>
 __device__ __forceinline__ void convert_tf32_inplace(uint8_t* base, int bytes, int ctid) {
   const uint32_t s0 = smem_u32(base);
   const int n = bytes >> 4;
-  // batches of 8 independent 16-byte accesses per thread (16 KB per batch for the 128 threads): the eight
+  // batches of 8 independent 16-byte accesses per thread (16 KB per batch for 128 threads): the eight
   // LDS.128 are in flight together, so a batch costs one shared-memory round trip instead of eight
   int i = ctid;
-  for (; i + 7 * 128 < n; i += 8 * 128) {
+  for (; i + 7 * NT < n; i += 8 * NT) {
     uint32_t v[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const uint32_t addr = s0 + 16u * (uint32_t)(i + j * 128);
+      const uint32_t addr = s0 + 16u * (uint32_t)(i + j * NT);
       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                    : "=r"(v[j][0]), "=r"(v[j][1]), "=r"(v[j][2]), "=r"(v[j][3])
                    : "r"(addr));
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const uint32_t addr = s0 + 16u * (uint32_t)(i + j * 128);
+      const uint32_t addr = s0 + 16u * (uint32_t)(i + j * NT);
       asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(tf32_half_ulp(v[j][0])),
                    "r"(tf32_half_ulp(v[j][1])), "r"(tf32_half_ulp(v[j][2])), "r"(tf32_half_ulp(v[j][3]))
                    : "memory");
     }
   }
-  for (; i < n; i += 128) {
+  for (; i < n; i += NT) {
     uint32_t a, b, c, d;
     const uint32_t addr = s0 + 16u * (uint32_t)i;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
@@ -149,8 +150,9 @@ struct FwdParams {
   float* partials;
 };
 
-// NU = K units per pipeline stage (one mbarrier round trip per stage), G = converter groups of 128 threads;
-// group g rounds stages g, g+G, ... so G stages are being rounded concurrently.
+// NU = K units per pipeline stage (one mbarrier round trip per stage), G = converter groups of 128 threads; all
+// 128 * G threads round every stage together (a 64 KB stage of the C = 512 off-diagonal tile takes as long to round
+// with 128 threads as its 8 MMAs take to run).
 template <int C, int NU, int G>
 struct FwdCfg {
   static constexpr int kBoxRows = (C == 64) ? 64 : (C == 128 ? 128 : 256);
@@ -159,8 +161,7 @@ struct FwdCfg {
   static constexpr int kUnitBytes = (C == 512) ? 65536 : (C == 256 ? 32768 : 16384);
   static constexpr int kStageBytes = NU * kUnitBytes;
   static constexpr int kStagesFit = (208 * 1024) / kStageBytes;
-  static constexpr int kStagesCap = kStagesFit > 12 ? 12 : kStagesFit;
-  static constexpr int kStages = kStagesCap - (kStagesCap % G);
+  static constexpr int kStages = kStagesFit > 12 ? 12 : kStagesFit;
   static constexpr int kThreads = 64 + 128 * G;
   static constexpr int kTmemCols = (C <= 128) ? 128 : 512;
   static constexpr int kTR = (C <= 256) ? C : 256;                     // partial tile edge
@@ -168,9 +169,6 @@ struct FwdCfg {
   static constexpr int kBarBytes = 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + kBarBytes;
   static_assert(kStages >= 2, "pipeline needs two stages");
-  // a converter group must always meet the same stage slots: with kStages % G != 0 a group can reach a slot whose
-  // previous fill (converted by ANOTHER group) has not landed yet and pass the parity wait spuriously
-  static_assert(kStages % G == 0 || G == 1, "kStages must be a multiple of the converter groups");
   static_assert((3 * kStages + 1) * 8 + 8 <= kBarBytes, "barrier area too small");
 };
 
@@ -205,7 +203,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) gram_fwd_tc_kernel(const __gr
     prefetch_tmap(&tmap);
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_conv + 8 * s, 128);
+      mbar_init(bar_conv + 8 * s, 128 * G);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_acc, 1);
@@ -300,18 +298,18 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) gram_fwd_tc_kernel(const __gr
   } else {
     // ===== converters (G groups of 128 threads), then epilogue =====
     const int grp = (warp - 2) >> 2;
-    const int ctid = (threadIdx.x - 64) & 127;
-    for (int i = grp; i < n_stages; i += G) {
+    const int ctid = threadIdx.x - 64;               // 0 .. 128 * G - 1
+    for (int i = 0; i < n_stages; ++i) {
       const int s = i % S;
       const uint32_t ph = (uint32_t)(i / S) & 1u;
       const int nu = min(NU, n_units - i * NU);
       mbar_wait(bar_full + 8 * s, ph);
       if (P.skip_rounding) {
       } else if (unit_tx_bytes == Cfg::kUnitBytes) {
-        convert_tf32_inplace(smem + s * Cfg::kStageBytes, nu * Cfg::kUnitBytes, ctid);
+        convert_tf32_inplace<128 * G>(smem + s * Cfg::kStageBytes, nu * Cfg::kUnitBytes, ctid);
       } else {
         for (int j = 0; j < nu; ++j)
-          convert_tf32_inplace(smem + s * Cfg::kStageBytes + j * Cfg::kUnitBytes, unit_tx_bytes, ctid);
+          convert_tf32_inplace<128 * G>(smem + s * Cfg::kStageBytes + j * Cfg::kUnitBytes, unit_tx_bytes, ctid);
       }
       fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(bar_conv + 8 * s);
@@ -554,6 +552,7 @@ struct BwdNhwcParams {
   float scale;
   const float* gscale;
   int accumulate;
+  int d_prerounded;  // D is already TF32-representable: the converters leave it alone
 };
 
 template <int C>
@@ -687,16 +686,17 @@ __global__ void __launch_bounds__(320, 1) gram_bwd_nhwc_tc_kernel(const __grid_c
     const int ctid = threadIdx.x - 64;
     if (Cfg::kResidentD) {
       mbar_wait(bar_dfull, 0);
-      convert_tf32_inplace(dres, Cfg::kDResBytes, ctid);
+      if (!P.d_prerounded) convert_tf32_inplace(dres, Cfg::kDResBytes, ctid);
       fence_proxy_async_smem();
       mbar_arrive(bar_dconv);
     }
     const int total = my_tiles * KC;
+    const int conv_bytes = P.d_prerounded ? Cfg::kFBytes : Cfg::kStageBytes;   // the F tile leads every stage
     for (int it = 0; it < total; ++it) {
       const int s = it % S;
       const uint32_t ph = (uint32_t)(it / S) & 1u;
       mbar_wait(bar_full + 8 * s, ph);
-      convert_tf32_inplace(smem + s * Cfg::kStageBytes, Cfg::kStageBytes, ctid);
+      convert_tf32_inplace(smem + s * Cfg::kStageBytes, conv_bytes, ctid);
       fence_proxy_async_smem();
       mbar_arrive(bar_conv + 8 * s);
     }
@@ -851,7 +851,7 @@ static void fwd_cfg(int C, int* nu, int* g) {
   // measured on B200 (profiles/r01_fwd_cfg_sweep.log): the four shapes are within 1 % of one another, so the
   // smallest one is the default
   *nu = env_nu ? env_nu : 1;
-  *g = env_g ? env_g : 1;
+  *g = env_g ? env_g : ((C == 512) ? 2 : 1);
   if (C >= 256) *nu = 1;   // a stage already holds 32/64 KB
 }
 
@@ -915,7 +915,7 @@ int gram_tc_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, f
 
 template <int C>
 static int launch_bwd_nhwc(const float* D, const float* F, int64_t HW, float scale, const float* gscale, float* dF,
-                           int accumulate, int num_sms, cudaStream_t stream) {
+                           int accumulate, int d_prerounded, int num_sms, cudaStream_t stream) {
   using Cfg = BwdNhwcCfg<C>;
   CUtensorMap tmF, tmD, tmO;
   int rc = make_tmap(&tmF, F, (uint64_t)HW, C, C, 128);
@@ -930,6 +930,7 @@ static int launch_bwd_nhwc(const float* D, const float* F, int64_t HW, float sca
   P.scale = scale;
   P.gscale = gscale;
   P.accumulate = accumulate;
+  P.d_prerounded = d_prerounded;
   cudaError_t e = cudaFuncSetAttribute(gram_bwd_nhwc_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes);
   if (e != cudaSuccess) {
@@ -942,12 +943,12 @@ static int launch_bwd_nhwc(const float* D, const float* F, int64_t HW, float sca
 }
 
 int gram_tc_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale, float* dF,
-                     int accumulate, int num_sms, cudaStream_t stream) {
+                     int accumulate, int d_prerounded, int num_sms, cudaStream_t stream) {
   switch (C) {
-    case 64: return launch_bwd_nhwc<64>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
-    case 128: return launch_bwd_nhwc<128>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
-    case 256: return launch_bwd_nhwc<256>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
-    case 512: return launch_bwd_nhwc<512>(D, F, HW, scale, gscale, dF, accumulate, num_sms, stream);
+    case 64: return launch_bwd_nhwc<64>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, num_sms, stream);
+    case 128: return launch_bwd_nhwc<128>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, num_sms, stream);
+    case 256: return launch_bwd_nhwc<256>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, num_sms, stream);
+    case 512: return launch_bwd_nhwc<512>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, num_sms, stream);
   }
   set_error("gram_tc_bwd_nhwc: unsupported C=%d", C);
   return AST_ERR_UNSUPPORTED;

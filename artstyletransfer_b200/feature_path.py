@@ -241,7 +241,8 @@ class LevelPathFn(torch.autograd.Function):
             f = taps[k]
             c, hw = f.shape[1], f.shape[2] * f.shape[3]
             d = torch.empty((c, c), dtype=torch.float32, device=dev)
-            ops.gram_mse_fwd_nhwc(f, c, hw, 1.0 / (c * hw), targets.grams[j], d, vals[j], wss.for_gram(j, c, hw, dev))
+            ops.gram_mse_fwd_nhwc(f, c, hw, 1.0 / (c * hw), targets.grams[j], d, vals[j], wss.for_gram(j, c, hw, dev),
+                                  round_out=True)     # D only feeds the backward's tensor-core operand
             ds[k] = d
         xc = taps[content_idx]
         if xc.numel() != targets.content_cl.numel():
@@ -274,7 +275,8 @@ class LevelPathFn(torch.autograd.Function):
             c, hw = tap.shape[1], tap.shape[2] * tap.shape[3]
             wrote = False
             if k in ds:
-                ops.gram_bwd_nhwc(ds[k], tap, c, hw, (sw / n) * 4.0 / (float(c) * c * c * hw), gsc, g, acc)
+                ops.gram_bwd_nhwc(ds[k], tap, c, hw, (sw / n) * 4.0 / (float(c) * c * c * hw), gsc, g, acc,
+                                  d_prerounded=True)
                 wrote = True
             if k == content_idx:
                 ops.mse_bwd(tap, targets.content_cl, cw * 2.0 / tap.numel(), gsc, g, acc or wrote)

@@ -192,10 +192,10 @@ def gram_mse_fwd(feat: torch.Tensor, C: int, HW: int, scale: float, target: Opti
 
 
 def gram_finalize(g_raw: torch.Tensor, C: int, scale: float, target: Optional[torch.Tensor], out: torch.Tensor,
-                  loss: Optional[torch.Tensor], ws: Workspace) -> None:
+                  loss: Optional[torch.Tensor], ws: Workspace, round_out: bool = False) -> None:
     _launch(g_raw.device, ('gram_finalize', C), 'ast_gram_finalize', g_raw.data_ptr(), C, scale,
             target.data_ptr() if target is not None else None, out.data_ptr(),
-            loss.data_ptr() if loss is not None else None, ws.ptr, ws.nbytes)
+            loss.data_ptr() if loss is not None else None, ws.ptr, ws.nbytes, int(round_out))
 
 
 def gram_bwd(D: torch.Tensor, feat: torch.Tensor, C: int, HW: int, scale: float, gscale: Optional[torch.Tensor],
@@ -209,18 +209,20 @@ def gram_bwd(D: torch.Tensor, feat: torch.Tensor, C: int, HW: int, scale: float,
 
 
 def gram_mse_fwd_nhwc(feat: torch.Tensor, C: int, HW: int, scale: float, target: Optional[torch.Tensor],
-                      out: torch.Tensor, loss: Optional[torch.Tensor], ws: Workspace, offset: int = 0) -> None:
-    """feat: (HW, C) row-major storage (torch channels_last); the operand starts `offset` elements in."""
+                      out: torch.Tensor, loss: Optional[torch.Tensor], ws: Workspace, offset: int = 0,
+                      round_out: bool = False) -> None:
+    """feat: (HW, C) row-major storage (torch channels_last); the operand starts `offset` elements in.
+    round_out: store `out` (= D) rounded to TF32 for gram_bwd_nhwc(..., d_prerounded=True)."""
     _launch(feat.device, ('gram_fwd_nhwc', C, HW), 'ast_gram_mse_fwd_nhwc', feat.data_ptr() + 4 * offset, C, HW, scale,
             target.data_ptr() if target is not None else None, out.data_ptr(),
-            loss.data_ptr() if loss is not None else None, ws.ptr, ws.nbytes)
+            loss.data_ptr() if loss is not None else None, ws.ptr, ws.nbytes, int(round_out))
 
 
 def gram_bwd_nhwc(D: torch.Tensor, feat: torch.Tensor, C: int, HW: int, scale: float, gscale: Optional[torch.Tensor],
-                  dF: torch.Tensor, accumulate: bool, offset: int = 0) -> None:
+                  dF: torch.Tensor, accumulate: bool, offset: int = 0, d_prerounded: bool = False) -> None:
     _launch(feat.device, ('gram_bwd_nhwc', C, HW, int(accumulate)), 'ast_gram_bwd_nhwc', D.data_ptr(),
             feat.data_ptr() + 4 * offset, C, HW, scale, gscale.data_ptr() if gscale is not None else None,
-            dF.data_ptr() + 4 * offset, int(accumulate))
+            dF.data_ptr() + 4 * offset, int(accumulate), int(d_prerounded))
 
 
 def _gscale(g: Optional[torch.Tensor], dev: torch.device) -> Optional[torch.Tensor]:

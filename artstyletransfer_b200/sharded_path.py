@@ -15,6 +15,7 @@ buffers (row 0 / row h+1 are the halos; at the image border they stay zero = the
 """
 from __future__ import annotations
 
+import os
 from typing import List, Sequence
 
 import torch
@@ -24,6 +25,46 @@ from . import ops
 from . import parallel as par
 
 _CL = torch.channels_last
+MULTI_STREAM = os.environ.get('AST_LEVEL_STREAMS', '1') != '0'
+
+
+class Lanes:
+    """Fork / join of the per-level work between two exchange points.  Lane 0 (the largest level) is the current
+    stream; every other level gets its own stream that waits for the fork point and is joined before the next
+    grouped exchange.  The pyramid levels' kernels are independent between exchanges, and the small levels' tiny
+    launches (a 32-row band of the 256x384 level is a handful of CTAs) disappear in the shadow of the big one's.
+    Inside a CUDA-graph capture the forks become parallel branches of the graph."""
+
+    def __init__(self, device: torch.device, n: int):
+        self.device = device
+        self.side = [torch.cuda.Stream(device) for _ in range(max(n - 1, 0))]
+
+    def each(self, indices, fn) -> None:
+        """fn(li) for every li in indices; li == indices[0] on the current stream, the rest on side streams."""
+        indices = list(indices)
+        if len(indices) <= 1 or not self.side:
+            for li in indices:
+                fn(li)
+            return
+        main = torch.cuda.current_stream(self.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        joins = []
+        for n, li in enumerate(indices[1:]):
+            st = self.side[n % len(self.side)]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                fn(li)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            joins.append(ev)
+        fn(indices[0])
+        for ev in joins:
+            main.wait_event(ev)
+
+
+_SERIAL = Lanes.__new__(Lanes)
+_SERIAL.device, _SERIAL.side = None, []
 
 
 def _rows(t: torch.Tensor) -> torch.Tensor:
@@ -56,7 +97,7 @@ class ShardedPathLevel:
         self.fin_ws = [ops.reduce_workspace(dev) for _ in self.sidx]
         # persistent padded activation bands: xin (the image band) and one per step
         c0 = plan.steps[0][3]
-        self.xin = torch.zeros((1, c0, self.hb + 2, width), dtype=torch.float32, device=dev).contiguous(memory_format=_CL)
+        self.xin = torch.empty((1, c0, self.hb + 2, width), dtype=torch.float32, device=dev, memory_format=_CL).zero_()
         self.bufs: List[torch.Tensor] = []
         c, h, w = c0, self.hb, width
         for sidx in range(plan.n_steps_needed):
@@ -65,7 +106,7 @@ class ShardedPathLevel:
                 c = st[4]
             else:
                 h, w = h // 2, w // 2
-            self.bufs.append(torch.zeros((1, c, h + 2, w), dtype=torch.float32, device=dev).contiguous(memory_format=_CL))
+            self.bufs.append(torch.empty((1, c, h + 2, w), dtype=torch.float32, device=dev, memory_format=_CL).zero_())
         self.generation = 0
 
     def build(self, level_img: torch.Tensor):
@@ -128,6 +169,7 @@ class ShardedPyramid:
 
     def __init__(self, levels: List[ShardedPathLevel]):
         self.levels = list(levels)
+        self.lanes = Lanes(levels[0].xin.device, len(levels)) if MULTI_STREAM else _SERIAL
 
     def evaluate(self, optimizing_img: torch.Tensor):
         """image leaf -> summed loss over the levels (neural_style_transfer.py:168-185), differentiable."""
@@ -145,26 +187,27 @@ class PyramidFn(torch.autograd.Function):
         imgs = [img.contiguous()]
         for i in range(1, len(pyr.levels)):
             imgs.append(ops.bicubic_down_raw(imgs[-1], imgs[-1].shape[-2] // 2, imgs[-1].shape[-1] // 2))
-        out4s, state = pyramid_forward(pyr.levels, imgs)
+        out4s, state = pyramid_forward(pyr.levels, imgs, pyr.lanes)
         total = out4s[0][0]
         for o in out4s[1:]:
             total = 1.0 * total + o[0]
         pyr.last_out4 = out4s
         if ctx.needs_input_grad[1]:
             ctx.state = state
+            ctx.lanes = pyr.lanes
             ctx.shapes = [tuple(t.shape[-2:]) for t in imgs]
         return total
 
     @staticmethod
     def backward(ctx, g_total):
         state, ctx.state = ctx.state, None
-        d_imgs = pyramid_backward(state, g_total)
+        d_imgs = pyramid_backward(state, g_total, ctx.lanes)
         for i in range(len(d_imgs) - 1, 0, -1):          # adjoint of the down-sampling chain, coarse -> fine
             ops.bicubic_down_adj_raw(d_imgs[i], *ctx.shapes[i - 1], gx=d_imgs[i - 1], accumulate=True)
         return None, d_imgs[0]
 
 
-def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Tensor]):
+def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Tensor], lanes: Lanes = _SERIAL):
     """Forward schedule of several sharded levels in lock-step (one level = the plain sharded level).
     Returns ([out4 per level], state for pyramid_backward)."""
     dev = ops._require_cuda(*imgs)
@@ -189,8 +232,8 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
         if st[0] == 'conv' and sidx > 0:
             with ops.timed(dev, ('halo_exchange_fwd', len(levels), sidx)):
                 par.halo_exchange(grp, [_rows(x) for x in xs])
-        for li, sh in enumerate(levels):
-            x, y = xs[li], sh.bufs[sidx]
+        def step(li, st=st, sidx=sidx):
+            x, y = xs[li], levels[li].bufs[sidx]
             if st[0] == 'conv':
                 yi = _interior(y)
                 _conv_fwd_into(x, st[1], yi)
@@ -200,14 +243,18 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
             for k in plan.taps_at.get(sidx, ()):
                 taps[li][k] = _interior(y)
             xs[li] = y
+
+        lanes.each(range(len(levels)), step)
     # raw partial Grams + partial content SSE of every level -> ONE all-reduce -> identical finalize on every rank
     n_packed = sum((sh.n_packed + 3) // 4 * 4 for sh in levels)      # every level's block stays 16-byte aligned
     packed_all = torch.zeros(n_packed, dtype=torch.float32, device=dev)
     packs, o = [], 0
-    for li, sh in enumerate(levels):
-        packed = packed_all[o:o + sh.n_packed]
+    for sh in levels:
+        packs.append(packed_all[o:o + sh.n_packed])
         o += (sh.n_packed + 3) // 4 * 4
-        packs.append(packed)
+
+    def partials(li):
+        sh, packed = levels[li], packs[li]
         for j, k in enumerate(sh.sidx):
             f = taps[li][k]
             c, hw_band = f.shape[1], f.shape[2] * f.shape[3]
@@ -215,6 +262,8 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
                                   sh.wss.for_gram(j, c, hw_band, dev))
         ops.mse_fwd(taps[li][sh.cidx], sh.target_content_band, 1.0, packed[sh.content_slot],
                     sh.wss.for_reduce('content', dev))
+
+    lanes.each(range(len(levels)), partials)
     with ops.timed(dev, ('allreduce_packed_grams', n_packed)):
         grp.all_reduce_sum(packed_all)
     out4s, per_level = [], []
@@ -231,7 +280,7 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
             hw_global = (sh.H // st_) * (sh.W // st_)
             d = torch.empty((c, c), dtype=torch.float32, device=dev)
             ops.gram_finalize(packed[sh.offs[j]:sh.offs[j] + c * c], c, 1.0 / (c * hw_global), sh.target_grams[j], d,
-                              vals[j], sh.fin_ws[j])
+                              vals[j], sh.fin_ws[j], round_out=True)
             ds[k] = (d, hw_global)
         torch.mul(packed[sh.content_slot], 1.0 / sh.content_numel_global, out=vals[n_style])
         sums2 = torch.empty(2, dtype=torch.float32, device=dev)
@@ -243,7 +292,7 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
     return out4s, per_level
 
 
-def pyramid_backward(state, g_total) -> List[torch.Tensor]:
+def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tensor]:
     """Backward schedule in lock-step: this rank's contribution to every level image's gradient (its band rows,
     plus the TV gradient on rank 0).  g_total: upstream scalar gradient (device tensor) or None."""
     levels = [st[0] for st in state]
@@ -259,7 +308,7 @@ def pyramid_backward(state, g_total) -> List[torch.Tensor]:
     def new_grad_band(like_interior):
         """Padded gradient band (1, C, h+2, w) for a tensor shaped like an activation band's interior."""
         _, c, h, w = like_interior.shape
-        return torch.empty((1, c, h + 2, w), dtype=torch.float32, device=dev).contiguous(memory_format=_CL)
+        return torch.empty((1, c, h + 2, w), dtype=torch.float32, device=dev, memory_format=_CL)
 
     def tap_grad(li, k, tap, gp):
         sh, _, ds, _, _ = state[li]
@@ -273,7 +322,8 @@ def pyramid_backward(state, g_total) -> List[torch.Tensor]:
         wrote = False
         if k in ds:
             d, hw_global = ds[k]
-            ops.gram_bwd_nhwc(d, tap, c, hw_band, (sw / n) * 4.0 / (float(c) * c * c * hw_global), gsc, g, acc)
+            ops.gram_bwd_nhwc(d, tap, c, hw_band, (sw / n) * 4.0 / (float(c) * c * c * hw_global), gsc, g, acc,
+                              d_prerounded=True)
             wrote = True
         if k == sh.cidx:
             ops.mse_bwd(tap, sh.target_content_band, cw * 2.0 / sh.content_numel_global, gsc, g, acc or wrote)
@@ -294,20 +344,23 @@ def pyramid_backward(state, g_total) -> List[torch.Tensor]:
     masked = [False] * len(levels)
     for sidx in range(plan.n_steps_needed - 1, -1, -1):
         st = plan.steps[sidx]
-        for li, sh in enumerate(levels):
-            for k in plan.taps_at.get(sidx, ()):
-                gps[li] = tap_grad(li, k, _interior(sh.bufs[sidx]), gps[li])
-        live = [li for li in range(len(levels)) if gps[li] is not None]
+        has_tap = bool(plan.taps_at.get(sidx))
+        live = [li for li in range(len(levels)) if gps[li] is not None or has_tap]
         if not live:
             continue
         if st[0] == 'conv':
-            for li in live:
+            def pre(li, sidx=sidx):              # tap gradients into the band, then the ReLU's backward in place
+                for k in plan.taps_at.get(sidx, ()):
+                    gps[li] = tap_grad(li, k, _interior(levels[li].bufs[sidx]), gps[li])
                 if not masked[li]:
                     ops.relu_bwd_(_interior(gps[li]), _interior(levels[li].bufs[sidx]))
                 masked[li] = False
+
+            lanes.each(live, pre)
             with ops.timed(dev, ('halo_exchange_bwd', len(live), sidx)):
                 par.halo_exchange(grp, [_rows(gps[li]) for li in live], zero_border=True)
-            for li in live:
+
+            def dgrad(li, st=st, sidx=sidx):
                 sh = levels[li]
                 x = sh.bufs[sidx - 1] if sidx > 0 else sh.xin
                 gxp = _conv_bwd_data_padded(gps[li], x, st[1])   # owned rows complete; its halo rows are not used
@@ -318,13 +371,20 @@ def pyramid_backward(state, g_total) -> List[torch.Tensor]:
                     ops.hwc_to_chw(gxp, d_imgs[li], c0, sh.hb * sh.W, True, plane=sh.H * sh.W, x_off=sh.W * c0,
                                    y_off=sh.band.r0 * sh.W)
                     gps[li] = None
+
+            lanes.each(live, dgrad)
         else:
             fuse = sidx > 0 and plan.steps[sidx - 1][0] == 'conv' and (sidx - 1) not in plan.taps_at
-            for li in live:
+
+            def pool(li, sidx=sidx, fuse=fuse):
                 sh = levels[li]
+                for k in plan.taps_at.get(sidx, ()):
+                    gps[li] = tap_grad(li, k, _interior(sh.bufs[sidx]), gps[li])
                 xi = _interior(sh.bufs[sidx - 1] if sidx > 0 else sh.xin)
                 gxp = new_grad_band(xi)
                 ops.maxpool2x2_bwd(_interior(gps[li]), xi, _interior(gxp), fuse)
                 masked[li] = fuse
                 gps[li] = gxp
+
+            lanes.each(live, pool)
     return d_imgs

@@ -50,6 +50,7 @@ def parse():
     ap.add_argument('--optimizer', default='adam', choices=['adam', 'lbfgs'])
     ap.add_argument('--precision', default=None, choices=[None, 'tf32', 'fp32'])
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--profile', default=None, help='write a torch.profiler kernel table of 3 timed-mode steps (rank 0) to this path')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -274,6 +275,17 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     closures = job.step - closures0
     graphed = job._graph is not None
+    if args.profile:
+        # device-side view of the graphed step (CUPTI sees the kernels a graph replay launches); not a timing source
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                job.optimizer_step()
+            torch.cuda.synchronize()
+        if rank == 0:
+            with open(args.profile, 'w') as f:
+                f.write(prof.key_averages().table(sort_by='cuda_time_total', row_limit=60, max_name_column_width=90))
+        barrier()
     # ---- per-kernel pass: the same closure launched eagerly with CUDA events around every C-ABI call ---------
     ops.STATS.reset(enabled=True, timing=True)
     probe_steps = 3

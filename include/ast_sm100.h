@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 1
+#define AST_ABI_VERSION 2
 
 #define AST_OK               0
 #define AST_ERR_INVALID     -1   /* bad argument (null pointer, non-positive size, misalignment) */
@@ -74,8 +74,10 @@ int ast_gram_tf32_supported(const float* F, int C, int64_t HW, int64_t ld);
 int ast_gram_mse_fwd(const float* F, int C, int64_t HW, int64_t ld, float scale, const float* A,
                      float* out, float* loss, void* ws, size_t ws_bytes, int precision,
                      void* stream);
+/* round_out != 0: `out` is stored rounded to nearest TF32 (the loss is still computed from the exact values).  Use it
+ * when `out` = D only feeds ast_gram_bwd_nhwc(..., d_prerounded = 1): the backward's converter warps then skip D. */
 int ast_gram_finalize(const float* G_raw, int C, float scale, const float* A, float* out,
-                      float* loss, void* ws, size_t ws_bytes, void* stream);
+                      float* loss, void* ws, size_t ws_bytes, int round_out, void* stream);
 
 /* Backward of the style term (autograd of bmm + MSELoss in the reference, 2 bmm per layer):
  *   dF[C,HW] (+)= scale * D D-symmetric [C,C] * F[C,HW]
@@ -91,9 +93,9 @@ int ast_gram_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, 
  * pointer).  TF32 operands only.  out/loss/ws as for ast_gram_mse_fwd; dF may alias nothing else.
  * accumulate != 0 adds into dF with TMA reduce-add (the SM never reads dF). */
 int ast_gram_mse_fwd_nhwc(const float* F, int C, int64_t HW, float scale, const float* A, float* out,
-                          float* loss, void* ws, size_t ws_bytes, void* stream);
+                          float* loss, void* ws, size_t ws_bytes, int round_out, void* stream);
 int ast_gram_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale,
-                      const float* gscale, float* dF, int accumulate, void* stream);
+                      const float* gscale, float* dF, int accumulate, int d_prerounded, void* stream);
 
 /* ---- Content MSE (neural_style_transfer.py:95) ---------------------------------------------
  *   *loss = scale * sum((X - T)^2)      (scale = 1/n for MSELoss(reduction='mean'))

@@ -61,6 +61,11 @@ def test_maxpool_fwd_bwd_matches_torch(c, h, w, relu_mask):
         gref = torch.where(x > 0, gref, torch.zeros_like(gref))
     assert not torch.isnan(gx).any()
     assert torch.equal(gx, gref)
+    # and against the numpy oracle (H, W, C arrays)
+    from oracle import gatys_oracle as O
+    hwc = lambda t: t[0].permute(1, 2, 0).cpu().numpy()
+    assert np.array_equal(hwc(y), O.maxpool2x2_hwc(hwc(x)))
+    assert np.array_equal(hwc(gx), O.maxpool2x2_bwd_hwc(hwc(gy), hwc(x), relu_mask))
 
 
 def test_image_layout_roundtrip():

@@ -105,3 +105,31 @@ def test_gram_nhwc_full_size_properties(c, hw):
     df2 = df.clone()
     ops.gram_bwd_nhwc(d, f, c, hw, 1.0, None, df2, True)   # accumulate: exactly doubles
     assert rel(df2[idx].cpu().numpy(), 2 * ref.cpu().numpy()) < 2e-3
+
+
+@pytest.mark.parametrize('c,hw', [(64, 4096 + 37), (128, 5000), (256, 3000), (512, 2500)])
+def test_prerounded_d_gives_bit_identical_backward(c, hw):
+    """round_out stores D already rounded to TF32 and d_prerounded lets the backward's converters skip it: the
+    tensor core must see exactly the same operand bits either way; the loss is computed from the exact D."""
+    from artstyletransfer_b200 import ops
+    f = _feat(c, hw, 17)
+    a = torch.rand((c, c), device=dev()) * 1e-3
+    a = (a + a.t()) / 2
+    ws = ops.gram_workspace(c, hw, dev())
+    d0 = torch.empty((c, c), device=dev()); d1 = torch.empty((c, c), device=dev())
+    l0 = torch.empty((), device=dev()); l1 = torch.empty((), device=dev())
+    ops.gram_mse_fwd_nhwc(f, c, hw, 1.0 / (c * hw), a, d0, l0, ws)
+    ops.gram_mse_fwd_nhwc(f, c, hw, 1.0 / (c * hw), a, d1, l1, ws, round_out=True)
+    assert l0.item() == l1.item()
+    assert rel(d1.cpu().numpy(), d0.cpu().numpy()) < 1e-3 and not torch.equal(d0, d1)
+    assert torch.equal(d1.view(torch.int32) & 0x1fff, torch.zeros_like(d1, dtype=torch.int32))
+    g0 = torch.empty_like(f); g1 = torch.empty_like(f)
+    ops.gram_bwd_nhwc(d0, f, c, hw, 3.0, None, g0, False)
+    ops.gram_bwd_nhwc(d1, f, c, hw, 3.0, None, g1, False, d_prerounded=True)
+    assert torch.equal(g0, g1)
+    # ast_gram_finalize has the same switch (sharded path)
+    raw = torch.empty((c, c), device=dev()); d2 = torch.empty((c, c), device=dev()); l2 = torch.empty((), device=dev())
+    ops.gram_mse_fwd_nhwc(f, c, hw, 1.0, None, raw, None, ws)
+    ops.gram_finalize(raw, c, 1.0 / (c * hw), a, d2, l2, ops.reduce_workspace(dev()), round_out=True)
+    assert torch.equal(d2.view(torch.int32) & 0x1fff, torch.zeros_like(d2, dtype=torch.int32))
+    assert rel(d2.cpu().numpy(), d0.cpu().numpy()) < 1e-3

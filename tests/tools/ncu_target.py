@@ -1,4 +1,7 @@
-"""Small target for `ncu --set full`: one forward + backward Gram launch per VGG width at the L=3 sizes."""
+"""Small target for `ncu --set full`: ONE launch of each hot kernel of the channels-last path at the L=3 top-level
+sizes (after one untimed warm-up launch each, which ncu skips with -s): the (HW, C) Gram forward / backward for the
+four VGG widths, the glue kernels on the largest activations, the content MSE, TV and the bicubic pyramid step.
+usage: python tests/tools/ncu_target.py [warm]   ('warm' = also do the warm-up launches, for a plain run)"""
 import os
 import sys
 
@@ -8,17 +11,51 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from artstyletransfer_b200 import ops  # noqa: E402
 
+CL = torch.channels_last
 dev = torch.device('cuda', 0)
-shapes = [(64, 6291456), (128, 1572864), (256, 393216), (512, 98304)]
-if len(sys.argv) > 1:
-    shapes = [s for s in shapes if str(s[0]) in sys.argv[1:]]
-for c, hw in shapes:
-    f = torch.relu(torch.randn((c, hw), device=dev)) * 0.25
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def once(fn):
+    flush.zero_()                      # evict L2 so the profiled launch reads HBM like it does inside a step
+    fn()
+
+
+for c, hw in [(64, 6291456), (128, 1572864), (256, 393216), (512, 98304)]:
+    f = torch.relu(torch.randn((hw, c), device=dev)) * 0.25
     a = torch.rand((c, c), device=dev) * 1e-3
-    d = torch.empty((c, c), device=dev); loss = torch.empty((), device=dev); df = torch.empty_like(f)
+    d = torch.empty((c, c), device=dev); loss = torch.empty((), device=dev); df = torch.zeros_like(f)
     ws = ops.gram_workspace(c, hw, dev)
-    for _ in range(2):
-        ops.gram_mse_fwd(f, c, hw, 1.0 / (c * hw), a, d, loss, ws, 0)
-        ops.gram_bwd(d, f, c, hw, 1e-3, None, df, False, 0)
+    once(lambda: ops.gram_mse_fwd_nhwc(f, c, hw, 1.0 / (c * hw), a, d, loss, ws))
+    once(lambda: ops.gram_bwd_nhwc(d, f, c, hw, 1e-3, None, df, False))
+    once(lambda: ops.gram_bwd_nhwc(d, f, c, hw, 1e-3, None, df, True))
     torch.cuda.synchronize()
     print(c, hw, float(loss))
+    del f, df
+
+# glue on relu1_x-sized activations (64 x 2048 x 3072 = 1.6 GB) and the pool after them
+y = torch.randn((1, 64, 2048, 3072), device=dev).contiguous(memory_format=CL)
+b = torch.randn(64, device=dev)
+g = torch.randn((1, 64, 2048, 3072), device=dev).contiguous(memory_format=CL)
+once(lambda: ops.bias_relu_(y, b))
+once(lambda: ops.relu_bwd_(g, y))
+p = torch.empty((1, 64, 1024, 1536), device=dev, memory_format=CL)
+once(lambda: ops.maxpool2x2(y, p))
+gp = torch.randn((1, 64, 1024, 1536), device=dev).contiguous(memory_format=CL)
+once(lambda: ops.maxpool2x2_bwd(gp, y, g, True))
+del y, g, p, gp
+# content MSE on relu4_2 (512 x 256 x 384), TV + pyramid step on the 2048 x 3072 image
+x = torch.randn(50331648, device=dev); t = torch.randn(50331648, device=dev); dx = torch.zeros_like(x)
+lossv = torch.empty((), device=dev)
+rws = ops.reduce_workspace(dev)
+once(lambda: ops.mse_fwd(x, t, 1.0 / x.numel(), lossv, rws))
+once(lambda: ops.mse_bwd(x, t, 2.0 / x.numel(), None, dx, True))
+img = torch.randn((1, 3, 2048, 3072), device=dev)
+sums2 = torch.empty(2, device=dev); tv = torch.empty((), device=dev); dimg = torch.empty_like(img)
+once(lambda: ops.tv_fwd(img, sums2, tv, rws))
+once(lambda: ops.tv_bwd(img, sums2, 1e2, None, dimg, False))
+half = [None]
+once(lambda: half.__setitem__(0, ops.bicubic_down_raw(img, 1024, 1536)))
+once(lambda: ops.bicubic_down_adj_raw(half[0], 2048, 3072, gx=dimg, accumulate=True))
+torch.cuda.synchronize()
+print('done')
