@@ -44,24 +44,36 @@ __global__ void __launch_bounds__(256) down2x_kernel(const float* __restrict__ x
   if (vec_ok) {
     // aligned float4 columns 2*e0-4 .. 2*e0+259 -> 66 float4 per row (W % 4 == 0, rows 16-byte aligned)
     constexpr int V = 66;
-    for (int idx = threadIdx.x; idx < D2_SROWS * V; idx += 256) {
+    constexpr int kIters = (D2_SROWS * V + 255) / 256;   // 9
+    float4 vals[kIters];
+    // all of the thread's 16-byte loads are issued before the first shared-memory store: 9 loads in flight per
+    // thread instead of 1 (the load -> store dependency otherwise serialises them and HBM latency bounds the kernel)
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int idx = threadIdx.x + it * 256;
       const int r = idx / V, v = idx - r * V;
-      const int gr = min(max(gr0 + r, 0), H - 1);
+      const int gr = min(max(gr0 + min(r, D2_SROWS - 1), 0), H - 1);
       const int c4 = 2 * e0 - 4 + 4 * v;
       const float* row = xp + (size_t)gr * W;
-      float4 val;
       if (c4 < 0) {
         const float e = __ldg(row);
-        val = make_float4(e, e, e, e);
+        vals[it] = make_float4(e, e, e, e);
       } else if (c4 < W) {
-        val = ldg_stream(reinterpret_cast<const float4*>(row + c4));
+        vals[it] = ldg_stream(reinterpret_cast<const float4*>(row + c4));
       } else {
         const float e = __ldg(row + W - 1);
-        val = make_float4(e, e, e, e);
+        vals[it] = make_float4(e, e, e, e);
       }
-      // columns c4, c4+2 are even -> E[2v-2 .. 2v-1] (+2); columns c4+1, c4+3 odd -> O[2v-1 .. 2v] (+1)
-      *reinterpret_cast<float2*>(tileE + r * D2_HALF + 2 * v) = make_float2(val.x, val.z);
-      *reinterpret_cast<float2*>(tileO + r * D2_HALF + 2 * v) = make_float2(val.y, val.w);
+    }
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int idx = threadIdx.x + it * 256;
+      if (idx < D2_SROWS * V) {
+        const int r = idx / V, v = idx - r * V;
+        // columns c4, c4+2 are even -> E[2v-2 .. 2v-1] (+2); columns c4+1, c4+3 odd -> O[2v-1 .. 2v] (+1)
+        *reinterpret_cast<float2*>(tileE + r * D2_HALF + 2 * v) = make_float2(vals[it].x, vals[it].z);
+        *reinterpret_cast<float2*>(tileO + r * D2_HALF + 2 * v) = make_float2(vals[it].y, vals[it].w);
+      }
     }
   } else {
     constexpr int SC = 2 * D2_TW + 2;  // local columns 0..257 <-> global 2*e0-1 .. 2*e0+256
@@ -103,7 +115,6 @@ __global__ void __launch_bounds__(256) down2x_kernel(const float* __restrict__ x
 // Per axis (m outputs, n = 2m inputs):
 //   out[2p]   = w1*g[p] + w3*g[p-1]   (+ w0*g[0]   folded from the clamped tap -1 when p == 0)
 //   out[2p+1] = w2*g[p] + w0*g[p+1]   (+ w3*g[m-1] folded from the clamped tap n  when p == m-1)
-// Thread = output-gradient row p, two output-gradient columns (q, q+1) -> writes 2 rows x float4 of gx.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void adj_axis_weights(int p, int m, float& c_m1, float& c_0e, float& c_0o, float& c_p1) {
   // contributions to (even, odd) input samples of position p from g[p-1], g[p], g[p+1]
@@ -113,62 +124,78 @@ __device__ __forceinline__ void adj_axis_weights(int p, int m, float& c_m1, floa
   c_p1 = (p + 1 <= m - 1) ? kTap[0] : 0.f;                // odd  <- g[p+1]
 }
 
+// Thread = output-gradient row p, FOUR output-gradient columns q0..q0+3 -> writes 2 rows x 8 floats of gx from a
+// 3 x 6 neighbourhood of gy (16-byte loads for the aligned middle four); block = 64 column quads x 4 rows.
 __global__ void __launch_bounds__(256) down2x_adj_kernel(const float* __restrict__ gy, int Ho, int Wo,
                                                         float* __restrict__ gx, int accumulate, int vec_ok) {
   const int W = 2 * Wo;
-  const int qpairs = (Wo + 1) >> 1;
-  const int64_t total = (int64_t)Ho * qpairs;
+  const int q0 = 4 * (blockIdx.x * 64 + (threadIdx.x & 63));
+  const int p = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (q0 >= Wo || p >= Ho) return;
   const float* gp = gy + (size_t)blockIdx.z * Ho * Wo;
   float* xp = gx + (size_t)blockIdx.z * (2 * Ho) * W;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int p = (int)(idx / qpairs);
-    const int q = 2 * (int)(idx - (int64_t)p * qpairs);
-    // vertical weights for rows 2p (even) and 2p+1 (odd)
-    float vy_m1, vy_0e, vy_0o, vy_p1;
-    adj_axis_weights(p, Ho, vy_m1, vy_0e, vy_0o, vy_p1);
-    // g columns q-1 .. q+2, vertically combined into even/odd input rows
-    float ge[4], go[4];
+  // vertical weights for rows 2p (even) and 2p+1 (odd)
+  float vy_m1, vy_0e, vy_0o, vy_p1;
+  adj_axis_weights(p, Ho, vy_m1, vy_0e, vy_0o, vy_p1);
+  // g rows p-1, p, p+1 at columns q0-1 .. q0+4
+  float ra[6], rb[6], rd[6];
+  const bool vec_in = vec_ok && (q0 + 3 < Wo);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = q - 1 + k;
-      float a = 0.f, b = 0.f, d = 0.f;
-      if (c >= 0 && c < Wo) {
-        b = __ldg(gp + (size_t)p * Wo + c);
-        if (p >= 1) a = __ldg(gp + (size_t)(p - 1) * Wo + c);
-        if (p + 1 < Ho) d = __ldg(gp + (size_t)(p + 1) * Wo + c);
-      }
-      ge[k] = vy_m1 * a + vy_0e * b;
-      go[k] = vy_0o * b + vy_p1 * d;
-    }
-    float r0[4], r1[4];
+  for (int rr = 0; rr < 3; ++rr) {
+    float* dst = rr == 0 ? ra : (rr == 1 ? rb : rd);
+    const int row = p - 1 + rr;
+    if (row < 0 || row >= Ho) {
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {  // the two output-gradient columns q+s
-      float hx_m1, hx_0e, hx_0o, hx_p1;
-      adj_axis_weights(q + s, Wo, hx_m1, hx_0e, hx_0o, hx_p1);
-      r0[2 * s] = hx_m1 * ge[s] + hx_0e * ge[s + 1];
-      r0[2 * s + 1] = hx_0o * ge[s + 1] + hx_p1 * ge[s + 2];
-      r1[2 * s] = hx_m1 * go[s] + hx_0e * go[s + 1];
-      r1[2 * s + 1] = hx_0o * go[s + 1] + hx_p1 * go[s + 2];
+      for (int k = 0; k < 6; ++k) dst[k] = 0.f;
+      continue;
     }
-    float* o0 = xp + (size_t)(2 * p) * W + 2 * q;
-    float* o1 = o0 + W;
-    if (vec_ok && q + 1 < Wo) {
-      float4 a = make_float4(r0[0], r0[1], r0[2], r0[3]);
-      float4 b = make_float4(r1[0], r1[1], r1[2], r1[3]);
+    const float* g = gp + (size_t)row * Wo;
+    dst[0] = (q0 >= 1) ? __ldg(g + q0 - 1) : 0.f;
+    if (vec_in) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(g + q0));
+      dst[1] = v.x; dst[2] = v.y; dst[3] = v.z; dst[4] = v.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dst[1 + k] = (q0 + k < Wo) ? __ldg(g + q0 + k) : 0.f;
+    }
+    dst[5] = (q0 + 4 < Wo) ? __ldg(g + q0 + 4) : 0.f;
+  }
+  float ge[6], go[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    ge[k] = vy_m1 * ra[k] + vy_0e * rb[k];
+    go[k] = vy_0o * rb[k] + vy_p1 * rd[k];
+  }
+  float r0[8], r1[8];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {  // the four output-gradient columns q0+s
+    float hx_m1, hx_0e, hx_0o, hx_p1;
+    adj_axis_weights(q0 + s, Wo, hx_m1, hx_0e, hx_0o, hx_p1);
+    r0[2 * s] = hx_m1 * ge[s] + hx_0e * ge[s + 1];
+    r0[2 * s + 1] = hx_0o * ge[s + 1] + hx_p1 * ge[s + 2];
+    r1[2 * s] = hx_m1 * go[s] + hx_0e * go[s + 1];
+    r1[2 * s + 1] = hx_0o * go[s + 1] + hx_p1 * go[s + 2];
+  }
+  float* o0 = xp + (size_t)(2 * p) * W + 2 * q0;
+  float* o1 = o0 + W;
+  if (vec_in) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 a = make_float4(r0[4 * h], r0[4 * h + 1], r0[4 * h + 2], r0[4 * h + 3]);
+      float4 b = make_float4(r1[4 * h], r1[4 * h + 1], r1[4 * h + 2], r1[4 * h + 3]);
       if (accumulate) {
-        const float4 pa = *reinterpret_cast<const float4*>(o0), pb = *reinterpret_cast<const float4*>(o1);
+        const float4 pa = *reinterpret_cast<const float4*>(o0 + 4 * h), pb = *reinterpret_cast<const float4*>(o1 + 4 * h);
         a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
         b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
       }
-      *reinterpret_cast<float4*>(o0) = a;
-      *reinterpret_cast<float4*>(o1) = b;
-    } else {
-      const int ncol = (q + 1 < Wo) ? 4 : 2;
-      for (int k = 0; k < ncol; ++k) {
-        o0[k] = accumulate ? o0[k] + r0[k] : r0[k];
-        o1[k] = accumulate ? o1[k] + r1[k] : r1[k];
-      }
+      *reinterpret_cast<float4*>(o0 + 4 * h) = a;
+      *reinterpret_cast<float4*>(o1 + 4 * h) = b;
+    }
+  } else {
+    const int ncol = 2 * min(4, Wo - q0);
+    for (int k = 0; k < ncol; ++k) {
+      o0[k] = accumulate ? o0[k] + r0[k] : r0[k];
+      o1[k] = accumulate ? o1[k] + r1[k] : r1[k];
     }
   }
 }
@@ -337,11 +364,10 @@ extern "C" int ast_bicubic_down2x_adj(const float* gy, int C, int H, int W, floa
               "ast_bicubic_down2x_adj: H and W must be even (got %dx%d); use ast_bicubic_resize_adj", H, W);
   AST_REQUIRE(C <= 65535, AST_ERR_INVALID, "ast_bicubic_down2x_adj: too many planes");
   const int Ho = H / 2, Wo = W / 2;
-  const int vec_ok = aligned16p(gx) && (W % 4 == 0);
-  const int64_t total = (int64_t)Ho * ((Wo + 1) / 2);
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  dim3 grid((unsigned)blocks, 1, C);
+  // 16-byte accesses need gy rows (Wo % 4 == 0) and gx rows (W % 8 == 0 follows) aligned
+  const int vec_ok = aligned16p(gx) && aligned16p(gy) && (Wo % 4 == 0);
+  dim3 grid((unsigned)(((Wo + 3) / 4 + 63) / 64), (unsigned)((Ho + 3) / 4), C);
+  AST_REQUIRE(grid.y <= 65535, AST_ERR_UNSUPPORTED, "ast_bicubic_down2x_adj: image too tall (%d rows)", H);
   down2x_adj_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gy, Ho, Wo, gx, accumulate, vec_ok);
   return check_launch("ast_bicubic_down2x_adj");
 }

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(kThreads) tv_fwd_kernel(const float* __restric
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
       const int y = (int)(row % H);
       const float* r = Y + row * W;
+#pragma unroll 4
       for (int xq = threadIdx.x; xq < w4; xq += blockDim.x) {
         const float* p = r + (xq << 2);
         const float4 a = ldg_stream(reinterpret_cast<const float4*>(p));
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(kThreads) tv_bwd_kernel(const float* __restric
     const int64_t rows = (int64_t)C * H;
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
      const int y = (int)(row % H);
+#pragma unroll 2
      for (int xq = threadIdx.x; xq < w4; xq += blockDim.x) {
       const float* p = Y + row * W + (xq << 2);
       const float4 a = __ldg(reinterpret_cast<const float4*>(p));
