@@ -42,10 +42,10 @@ SIGNATURES = {
     'ast_gram_finalize': (_i, [_p, _i, _f, _p, _p, _p, _p, _sz, _i, _p]),
     'ast_gram_bwd': (_i, [_p, _p, _i, _i64, _i64, _f, _p, _p, _i, _i, _p]),
     'ast_gram_mse_fwd_nhwc': (_i, [_p, _i, _i64, _f, _p, _p, _p, _p, _sz, _i, _p]),
-    'ast_gram_bwd_nhwc': (_i, [_p, _p, _i, _i64, _f, _p, _p, _i, _i, _p]),
+    'ast_gram_bwd_nhwc': (_i, [_p, _p, _i, _i64, _f, _p, _p, _i, _i, _i, _p]),
     'ast_reduce_workspace_bytes': (_sz, []),
     'ast_mse_fwd': (_i, [_p, _p, _i64, _f, _p, _p, _sz, _p]),
-    'ast_mse_bwd': (_i, [_p, _p, _i64, _f, _p, _p, _i, _p]),
+    'ast_mse_bwd': (_i, [_p, _p, _i64, _f, _p, _p, _i, _i, _p]),
     'ast_bias_relu_nhwc': (_i, [_p, _p, _i, _i64, _p]),
     'ast_relu_bwd': (_i, [_p, _p, _i64, _p]),
     'ast_maxpool2x2_nhwc': (_i, [_p, _i, _i, _i, _p, _p]),

@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(kThreads) mse_fwd_kernel(const float* __restri
 __global__ void __launch_bounds__(kThreads) mse_bwd_kernel(const float* __restrict__ X, const float* __restrict__ T,
                                                           int64_t n, int vec_ok, float scale,
                                                           const float* __restrict__ gscale, float* __restrict__ dX,
-                                                          int accumulate) {
+                                                          int accumulate, int relu_mask) {
+  // relu_mask: X is a ReLU output; its backward (X > 0) is applied to the accumulated gradient in the same pass
   if (gscale) scale *= __ldg(gscale);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -73,13 +74,18 @@ __global__ void __launch_bounds__(kThreads) mse_bwd_kernel(const float* __restri
         const float4 o = D4[i];
         g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
       }
+      if (relu_mask) {
+        g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f;
+        g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+      }
       D4[i] = g;
     }
     done = n4 << 2;
   }
   for (int64_t i = done + tid; i < n; i += nthreads) {
-    const float g = scale * (X[i] - T[i]);
-    dX[i] = accumulate ? dX[i] + g : g;
+    float g = scale * (X[i] - T[i]);
+    if (accumulate) g += dX[i];
+    dX[i] = (relu_mask && !(X[i] > 0.f)) ? 0.f : g;
   }
 }
 
@@ -246,13 +252,14 @@ extern "C" int ast_mse_fwd(const float* X, const float* T, int64_t n, float scal
 }
 
 extern "C" int ast_mse_bwd(const float* X, const float* T, int64_t n, float scale, const float* gscale, float* dX,
-                           int accumulate, void* stream) {
+                           int accumulate, int relu_mask, void* stream) {
   AST_REQUIRE(X && T && dX, AST_ERR_INVALID, "ast_mse_bwd: null pointer");
   AST_REQUIRE(n > 0, AST_ERR_INVALID, "ast_mse_bwd: n must be positive (got %lld)", (long long)n);
   const int vec_ok = aligned16(X) && aligned16(T) && aligned16(dX);
   int64_t blocks = (n + (int64_t)kThreads * 8 - 1) / ((int64_t)kThreads * 8);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  mse_bwd_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(X, T, n, vec_ok, scale, gscale, dX, accumulate);
+  mse_bwd_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(X, T, n, vec_ok, scale, gscale, dX, accumulate,
+                                                                     relu_mask ? 1 : 0);
   return check_launch("ast_mse_bwd");
 }
 

@@ -359,14 +359,15 @@ extern "C" int ast_gram_mse_fwd_nhwc(const float* F, int C, int64_t HW, float sc
 }
 
 extern "C" int ast_gram_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale,
-                                 float* dF, int accumulate, int d_prerounded, void* stream_) {
+                                 float* dF, int accumulate, int d_prerounded, int relu_mask, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   AST_REQUIRE(D && F && dF, AST_ERR_INVALID, "ast_gram_bwd_nhwc: null pointer");
   AST_REQUIRE(HW > 0 && HW <= (int64_t)0x7fffff00, AST_ERR_INVALID, "ast_gram_bwd_nhwc: bad HW=%lld", (long long)HW);
   AST_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, AST_ERR_UNSUPPORTED,
               "ast_gram_bwd_nhwc: C must be 64, 128, 256 or 512 (got %d)", C);
   AST_REQUIRE(is16(F) && is16(D) && is16(dF), AST_ERR_INVALID, "ast_gram_bwd_nhwc: D/F/dF must be 16-byte aligned");
-  return gram_tc_bwd_nhwc(D, F, C, HW, scale, gscale, dF, accumulate, d_prerounded ? 1 : 0, cached_num_sms(), stream);
+  return gram_tc_bwd_nhwc(D, F, C, HW, scale, gscale, dF, accumulate, d_prerounded ? 1 : 0, relu_mask ? 1 : 0,
+                          cached_num_sms(), stream);
 }
 
 extern "C" int ast_gram_finalize(const float* G_raw, int C, float scale, const float* A, float* out, float* loss,

@@ -40,7 +40,8 @@ int gram_tc_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, f
 // (HW, C) layout: dF[p, c] (+)= scale * sum_k F[p, k] D[c, k]
 // d_prerounded: D already holds TF32-representable values (ast_gram_mse_fwd_nhwc / ast_gram_finalize with round_out),
 // so the kernel's converter warps skip it (for C >= 256 D is 2/3 .. 4/5 of every staged chunk).
+// relu_mask: also apply the backward of the ReLU whose output F is: dF = (accumulate ? dF + v : v) * (F > 0).
 int gram_tc_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale, float* dF,
-                     int accumulate, int d_prerounded, int num_sms, cudaStream_t stream);
+                     int accumulate, int d_prerounded, int relu_mask, int num_sms, cudaStream_t stream);
 
 }  // namespace ast

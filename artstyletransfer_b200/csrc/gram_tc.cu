@@ -553,6 +553,10 @@ struct BwdNhwcParams {
   const float* gscale;
   int accumulate;
   int d_prerounded;  // D is already TF32-representable: the converters leave it alone
+  int relu_mask;     // fuse the backward of the ReLU that produced F: out = (accumulate ? dF + v : v) * (F > 0)
+  const float* F;    // (HW, C), read again by the epilogue when relu_mask is set (L2-hot: the tile was just staged)
+  float* dF;
+  int C;
 };
 
 template <int C>
@@ -720,21 +724,48 @@ __global__ void __launch_bounds__(320, 1) gram_bwd_nhwc_tc_kernel(const __grid_c
       for (int g = 0; g < C / 32; ++g) {
         tmem_ld_x32(lane_addr + b * C + g * 32, v);
         tmem_ld_wait();
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = scale * __uint_as_float(v[j]);
+        if (P.relu_mask) {
+          // Fused ReLU backward (+ running gradient).  This thread's position row, 32 channels = one 128-byte line
+          // of F (L2-hot: the tile was just staged) and of dF; all 16 loads are in flight together.  (A variant
+          // that re-walks the staged block with 8 lanes per row for coalesced loads was 2x SLOWER on B200: with
+          // 4 epilogue warps per SM the loads in flight, not the sectors per request, bound this path.  The
+          // planned version takes the mask from the converter warps and dF through a TMA load ring.)
+          const int64_t p = p0 + lane;
+          if (p < P.HW) {
+            const float4* fr = reinterpret_cast<const float4*>(P.F + p * C + g * 32);
+            const float4* gr = reinterpret_cast<const float4*>(P.dF + p * C + g * 32);
+            float4 f[8], q[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[j] = __ldg(fr + j);
+              q[j] = P.accumulate ? gr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              o[4 * j] = f[j].x > 0.f ? o[4 * j] + q[j].x : 0.f;
+              o[4 * j + 1] = f[j].y > 0.f ? o[4 * j + 1] + q[j].y : 0.f;
+              o[4 * j + 2] = f[j].z > 0.f ? o[4 * j + 2] + q[j].z : 0.f;
+              o[4 * j + 3] = f[j].w > 0.f ? o[4 * j + 3] + q[j].w : 0.f;
+            }
+          }
+        }
         if (lane == 0) tma_store_wait_read<1>();    // the block stored two rounds ago has left shared memory
         __syncwarp();
         const uint32_t buf = stg + (nbuf & 1u) * 4096u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t addr = buf + row_off + ((((uint32_t)j) ^ sw) << 4);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                       "f"(scale * __uint_as_float(v[4 * j])), "f"(scale * __uint_as_float(v[4 * j + 1])),
-                       "f"(scale * __uint_as_float(v[4 * j + 2])), "f"(scale * __uint_as_float(v[4 * j + 3]))
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[4 * j]), "f"(o[4 * j + 1]),
+                       "f"(o[4 * j + 2]), "f"(o[4 * j + 3])
                        : "memory");
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && p0 < P.HW) {
-          if (P.accumulate) tma_reduce_add_2d(&tmapO, buf, g * 32, (int)p0);
+          if (P.accumulate && !P.relu_mask) tma_reduce_add_2d(&tmapO, buf, g * 32, (int)p0);   // add happens in L2
           else tma_store_2d(&tmapO, buf, g * 32, (int)p0);
           tma_store_commit();
         }
@@ -915,7 +946,7 @@ int gram_tc_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, f
 
 template <int C>
 static int launch_bwd_nhwc(const float* D, const float* F, int64_t HW, float scale, const float* gscale, float* dF,
-                           int accumulate, int d_prerounded, int num_sms, cudaStream_t stream) {
+                           int accumulate, int d_prerounded, int relu_mask, int num_sms, cudaStream_t stream) {
   using Cfg = BwdNhwcCfg<C>;
   CUtensorMap tmF, tmD, tmO;
   int rc = make_tmap(&tmF, F, (uint64_t)HW, C, C, 128);
@@ -931,6 +962,10 @@ static int launch_bwd_nhwc(const float* D, const float* F, int64_t HW, float sca
   P.gscale = gscale;
   P.accumulate = accumulate;
   P.d_prerounded = d_prerounded;
+  P.relu_mask = relu_mask;
+  P.F = F;
+  P.dF = dF;
+  P.C = C;
   cudaError_t e = cudaFuncSetAttribute(gram_bwd_nhwc_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes);
   if (e != cudaSuccess) {
@@ -943,12 +978,12 @@ static int launch_bwd_nhwc(const float* D, const float* F, int64_t HW, float sca
 }
 
 int gram_tc_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale, float* dF,
-                     int accumulate, int d_prerounded, int num_sms, cudaStream_t stream) {
+                     int accumulate, int d_prerounded, int relu_mask, int num_sms, cudaStream_t stream) {
   switch (C) {
-    case 64: return launch_bwd_nhwc<64>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, num_sms, stream);
-    case 128: return launch_bwd_nhwc<128>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, num_sms, stream);
-    case 256: return launch_bwd_nhwc<256>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, num_sms, stream);
-    case 512: return launch_bwd_nhwc<512>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, num_sms, stream);
+    case 64: return launch_bwd_nhwc<64>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
+    case 128: return launch_bwd_nhwc<128>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
+    case 256: return launch_bwd_nhwc<256>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
+    case 512: return launch_bwd_nhwc<512>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
   }
   set_error("gram_tc_bwd_nhwc: unsupported C=%d", C);
   return AST_ERR_UNSUPPORTED;

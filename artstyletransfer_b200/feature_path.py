@@ -5,15 +5,17 @@ What the reference does per level and closure (neural_style_transfer.py:84-112 +
 `backward()` through all of it.  Here the same arithmetic runs as an explicit schedule with no autograd graph:
 
   forward   image (1,3,H,W) planar -> (H,W,3)            ast_chw_to_hwc
-            13 x [ cuDNN conv (torch op, out of scope)   aten.cudnn_convolution on channels_last tensors: the TF32
-                   bias + ReLU in place ]                tensor-core kernels run without NCHW<->NHWC transposes
+            13 x cuDNN conv + bias + ReLU (torch op,     aten.cudnn_convolution_relu on channels_last tensors: the TF32
+                 out of scope)                           tensor-core kernels run without NCHW<->NHWC transposes and
+                                                         apply the epilogue (sharded path: conv.out + ast_bias_relu_nhwc)
             4  x 2x2 max-pool                            ast_maxpool2x2_nhwc (no index tensor)
             5  x Gram + MSE on (HW, C) taps              ast_gram_mse_fwd_nhwc  (tcgen05, split-K, fused finalize)
             content MSE, TV, weighted sum                ast_mse_fwd, ast_tv_fwd, ast_level_combine
   backward  deepest tap first: dF (+)= s (G-A) F         ast_gram_bwd_nhwc (accumulates into the running gradient
                                                          with TMA reduce-add: no separate add kernels)
             content: dX += 2 w (X-T)/n                   ast_mse_bwd(accumulate)
-            ReLU backward in place / fused into pool bwd ast_relu_bwd, ast_maxpool2x2_bwd_nhwc
+            ReLU backward: fused into the tap kernels    relu_mask of ast_gram_bwd_nhwc / ast_mse_bwd (6 tap layers),
+            above, into the pool backward, else in place ast_maxpool2x2_bwd_nhwc (4), ast_relu_bwd (3)
             conv backward-data (cuDNN, torch op)         aten.convolution_backward(output_mask = input only)
             (H,W,3) -> planar image gradient, += TV grad ast_hwc_to_chw, ast_tv_bwd(accumulate)
 
@@ -35,6 +37,25 @@ _CL = torch.channels_last
 # so the unsharded path lets cuDNN apply the epilogue.  '0' = separate bias/ReLU kernel (what the sharded path uses:
 # its convolutions write straight into padded band buffers through cudnn_convolution.out).
 FUSED_CONV_RELU = os.environ.get('AST_FUSED_CONV_RELU', '1') != '0'
+# '1': let cuDNN time its engines once per convolution shape (torch.backends.cudnn.benchmark semantics, applied only
+# around this path's own calls) instead of trusting its heuristics.  Off by default like in the reference.
+CUDNN_BENCHMARK = os.environ.get('AST_CUDNN_BENCHMARK', '0') == '1'
+# widest tap whose ReLU backward is fused into ast_gram_bwd_nhwc's epilogue (wider taps run ast_relu_bwd afterwards)
+FUSED_TAP_RELU_MAX_C = int(os.environ.get('AST_FUSED_TAP_RELU_MAX_C', '256'))
+
+
+class _cudnn_mode:
+    """torch.backends.cudnn.benchmark = CUDNN_BENCHMARK for the duration of one cuDNN call of this path."""
+    __slots__ = ('old',)
+
+    def __enter__(self):
+        self.old = torch.backends.cudnn.benchmark
+        if CUDNN_BENCHMARK and not self.old:
+            torch.backends.cudnn.benchmark = True
+
+    def __exit__(self, *exc):
+        if torch.backends.cudnn.benchmark != self.old:
+            torch.backends.cudnn.benchmark = self.old
 
 
 class FeaturePlan:
@@ -114,18 +135,18 @@ def _ckey(kind, x, w):
 
 def _conv_fwd(x, w):
     with ops.timed(x.device, _ckey('cudnn_conv_fwd', x, w)):
-        return torch.ops.aten.cudnn_convolution(x, w, [1, 1], [1, 1], [1, 1], 1, False, False,
+        return torch.ops.aten.cudnn_convolution(x, w, [1, 1], [1, 1], [1, 1], 1, CUDNN_BENCHMARK, False,
                                                 torch.backends.cudnn.allow_tf32)
 
 
 def _conv_relu_fwd(x, w, b):
-    with ops.timed(x.device, _ckey('cudnn_conv_bias_relu_fwd', x, w)):
+    with ops.timed(x.device, _ckey('cudnn_conv_bias_relu_fwd', x, w)), _cudnn_mode():
         y = torch.cudnn_convolution_relu(x, w, b, [1, 1], [1, 1], [1, 1], 1)
     return y if y.is_contiguous(memory_format=_CL) else y.contiguous(memory_format=_CL)
 
 
 def _conv_bwd_data(g, x, w):
-    with ops.timed(x.device, _ckey('cudnn_conv_dgrad', x, w)):
+    with ops.timed(x.device, _ckey('cudnn_conv_dgrad', x, w)), _cudnn_mode():
         gi = torch.ops.aten.convolution_backward(g, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
                                                  [True, False, False])[0]
     return gi if gi.is_contiguous(memory_format=_CL) else gi.contiguous(memory_format=_CL)
@@ -164,16 +185,21 @@ def features_forward(plan: FeaturePlan, img: torch.Tensor, keep: bool):
 
 
 def features_backward(plan: FeaturePlan, saved, tap_grad, d_img: torch.Tensor, accumulate: bool) -> None:
-    """Back-propagates through the feature path.  tap_grad(k, tap, g) must add tap k's loss gradient into g
-    (a channels_last tensor like `tap`), allocating it when g is None, and return it.  The image gradient is
-    written (or added) into the planar (1,3,H,W) tensor d_img."""
+    """Back-propagates through the feature path.  tap_grad(k, tap, g, relu_mask) must add tap k's loss gradient
+    into g (a channels_last tensor like `tap`), allocating it when g is None, and return it; with relu_mask it
+    must also apply the backward of the ReLU that produced `tap` (fused into the same kernel).  The image gradient
+    is written (or added) into the planar (1,3,H,W) tensor d_img."""
     g = None
     masked = False       # the ReLU backward of the step below has already been applied (fused into pool backward)
     for sidx in range(plan.n_steps_needed - 1, -1, -1):
         st = plan.steps[sidx]
         x, y = saved[sidx]
-        for k in plan.taps_at.get(sidx, ()):
-            g = tap_grad(k, y, g)
+        taps_here = plan.taps_at.get(sidx, ())
+        for n, k in enumerate(taps_here):
+            # the last tap gradient added at a conv step also applies that step's ReLU backward
+            fuse = st[0] == 'conv' and n == len(taps_here) - 1 and not masked
+            g = tap_grad(k, y, g, fuse)
+            masked = masked or fuse
         if g is None:
             continue
         if st[0] == 'conv':
@@ -268,21 +294,23 @@ class LevelPathFn(torch.autograd.Function):
         gsc = ops._gscale(g_total, dev)
         n = len(style_idx)
 
-        def tap_grad(k, tap, g):
+        def tap_grad(k, tap, g, relu_mask):
             acc = g is not None
             if not acc:
                 g = torch.empty_like(tap, memory_format=_CL)
             c, hw = tap.shape[1], tap.shape[2] * tap.shape[3]
-            wrote = False
-            if k in ds:
+            style, content = k in ds, k == content_idx
+            # the Gram kernel's fused ReLU backward pays off up to C = 256 (measured, profiles/r01_gram_nhwc_sweep.jsonl)
+            fuse_gram = relu_mask and not content and c <= FUSED_TAP_RELU_MAX_C
+            if style:
                 ops.gram_bwd_nhwc(ds[k], tap, c, hw, (sw / n) * 4.0 / (float(c) * c * c * hw), gsc, g, acc,
-                                  d_prerounded=True)
-                wrote = True
-            if k == content_idx:
-                ops.mse_bwd(tap, targets.content_cl, cw * 2.0 / tap.numel(), gsc, g, acc or wrote)
-                wrote = True
-            if not wrote and not acc:
+                                  d_prerounded=True, relu_mask=fuse_gram)
+            if content:
+                ops.mse_bwd(tap, targets.content_cl, cw * 2.0 / tap.numel(), gsc, g, acc or style, relu_mask)
+            elif not style and not acc:
                 g.zero_()
+            if relu_mask and not content and not fuse_gram:
+                ops.relu_bwd_(g, tap)
             return g
 
         d_img = torch.empty_like(img)

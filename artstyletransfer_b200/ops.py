@@ -219,10 +219,13 @@ def gram_mse_fwd_nhwc(feat: torch.Tensor, C: int, HW: int, scale: float, target:
 
 
 def gram_bwd_nhwc(D: torch.Tensor, feat: torch.Tensor, C: int, HW: int, scale: float, gscale: Optional[torch.Tensor],
-                  dF: torch.Tensor, accumulate: bool, offset: int = 0, d_prerounded: bool = False) -> None:
-    _launch(feat.device, ('gram_bwd_nhwc', C, HW, int(accumulate)), 'ast_gram_bwd_nhwc', D.data_ptr(),
-            feat.data_ptr() + 4 * offset, C, HW, scale, gscale.data_ptr() if gscale is not None else None,
-            dF.data_ptr() + 4 * offset, int(accumulate), int(d_prerounded))
+                  dF: torch.Tensor, accumulate: bool, offset: int = 0, d_prerounded: bool = False,
+                  relu_mask: bool = False) -> None:
+    """relu_mask: feat is a ReLU output; write the gradient w.r.t. the ReLU's input (threshold_backward fused)."""
+    _launch(feat.device, ('gram_bwd_nhwc', C, HW, int(accumulate) + 2 * int(relu_mask)), 'ast_gram_bwd_nhwc',
+            D.data_ptr(), feat.data_ptr() + 4 * offset, C, HW, scale,
+            gscale.data_ptr() if gscale is not None else None, dF.data_ptr() + 4 * offset, int(accumulate),
+            int(d_prerounded), int(relu_mask))
 
 
 def _gscale(g: Optional[torch.Tensor], dev: torch.device) -> Optional[torch.Tensor]:
@@ -347,9 +350,9 @@ def mse_fwd(x, t, scale, loss, ws):
             loss.data_ptr(), ws.ptr, ws.nbytes)
 
 
-def mse_bwd(x, t, scale, gscale, dx, accumulate):
+def mse_bwd(x, t, scale, gscale, dx, accumulate, relu_mask=False):
     _launch(x.device, ('mse_bwd', x.numel()), 'ast_mse_bwd', x.data_ptr(), t.data_ptr(), x.numel(), scale,
-            gscale.data_ptr() if gscale is not None else None, dx.data_ptr(), int(accumulate))
+            gscale.data_ptr() if gscale is not None else None, dx.data_ptr(), int(accumulate), int(relu_mask))
 
 
 class ContentLossFn(torch.autograd.Function):

@@ -119,13 +119,13 @@ def _interior(buf: torch.Tensor) -> torch.Tensor:
 
 def _conv_fwd_into(x_pad, w, out):
     with ops.timed(x_pad.device, fp._ckey('cudnn_conv_fwd', out, w)):
-        torch.ops.aten.cudnn_convolution.out(x_pad, w, [0, 1], [1, 1], [1, 1], 1, False, False,
+        torch.ops.aten.cudnn_convolution.out(x_pad, w, [0, 1], [1, 1], [1, 1], 1, fp.CUDNN_BENCHMARK, False,
                                              torch.backends.cudnn.allow_tf32, out=out)
 
 
 def _conv_bwd_data_padded(g_pad, x_pad, w):
     """Backward-data over the whole padded band (h + 2 rows in, h + 2 rows out, symmetric padding)."""
-    with ops.timed(x_pad.device, fp._ckey('cudnn_conv_dgrad', g_pad, w)):
+    with ops.timed(x_pad.device, fp._ckey('cudnn_conv_dgrad', g_pad, w)), fp._cudnn_mode():
         gi = torch.ops.aten.convolution_backward(g_pad, x_pad, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
                                                  [True, False, False])[0]
     return gi if gi.is_contiguous(memory_format=_CL) else gi.contiguous(memory_format=_CL)
@@ -310,7 +310,7 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tenso
         _, c, h, w = like_interior.shape
         return torch.empty((1, c, h + 2, w), dtype=torch.float32, device=dev, memory_format=_CL)
 
-    def tap_grad(li, k, tap, gp):
+    def tap_grad(li, k, tap, gp, relu_mask):
         sh, _, ds, _, _ = state[li]
         cw, sw, tvw = sh.weights
         n = len(sh.sidx)
@@ -319,17 +319,19 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tenso
             gp = new_grad_band(tap)
         g = _interior(gp)
         c, hw_band = tap.shape[1], tap.shape[2] * tap.shape[3]
-        wrote = False
-        if k in ds:
+        style, content = k in ds, k == sh.cidx
+        fuse_gram = relu_mask and not content and c <= fp.FUSED_TAP_RELU_MAX_C
+        if style:
             d, hw_global = ds[k]
             ops.gram_bwd_nhwc(d, tap, c, hw_band, (sw / n) * 4.0 / (float(c) * c * c * hw_global), gsc, g, acc,
-                              d_prerounded=True)
-            wrote = True
-        if k == sh.cidx:
-            ops.mse_bwd(tap, sh.target_content_band, cw * 2.0 / sh.content_numel_global, gsc, g, acc or wrote)
-            wrote = True
-        if not wrote and not acc:
+                              d_prerounded=True, relu_mask=fuse_gram)
+        if content:
+            ops.mse_bwd(tap, sh.target_content_band, cw * 2.0 / sh.content_numel_global, gsc, g, acc or style,
+                        relu_mask)
+        elif not style and not acc:
             g.zero_()
+        if relu_mask and not content and not fuse_gram:
+            ops.relu_bwd_(g, tap)
         return gp
 
     d_imgs = []
@@ -349,9 +351,12 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tenso
         if not live:
             continue
         if st[0] == 'conv':
-            def pre(li, sidx=sidx):              # tap gradients into the band, then the ReLU's backward in place
-                for k in plan.taps_at.get(sidx, ()):
-                    gps[li] = tap_grad(li, k, _interior(levels[li].bufs[sidx]), gps[li])
+            def pre(li, sidx=sidx):              # tap gradients into the band + the ReLU's backward (fused or in place)
+                taps_here = plan.taps_at.get(sidx, ())
+                for n, k in enumerate(taps_here):
+                    fuse = n == len(taps_here) - 1 and not masked[li]
+                    gps[li] = tap_grad(li, k, _interior(levels[li].bufs[sidx]), gps[li], fuse)
+                    masked[li] = masked[li] or fuse
                 if not masked[li]:
                     ops.relu_bwd_(_interior(gps[li]), _interior(levels[li].bufs[sidx]))
                 masked[li] = False
@@ -379,7 +384,7 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tenso
             def pool(li, sidx=sidx, fuse=fuse):
                 sh = levels[li]
                 for k in plan.taps_at.get(sidx, ()):
-                    gps[li] = tap_grad(li, k, _interior(sh.bufs[sidx]), gps[li])
+                    gps[li] = tap_grad(li, k, _interior(sh.bufs[sidx]), gps[li], False)
                 xi = _interior(sh.bufs[sidx - 1] if sidx > 0 else sh.xin)
                 gxp = new_grad_band(xi)
                 ops.maxpool2x2_bwd(_interior(gps[li]), xi, _interior(gxp), fuse)

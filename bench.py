@@ -50,6 +50,8 @@ def parse():
     ap.add_argument('--optimizer', default='adam', choices=['adam', 'lbfgs'])
     ap.add_argument('--precision', default=None, choices=[None, 'tf32', 'fp32'])
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cudnn-autotune', action='store_true',
+                    help='leave cuDNN on its heuristics (default: time its engines once per convolution shape)')
     ap.add_argument('--profile', default=None, help='write a torch.profiler kernel table of 3 timed-mode steps (rank 0) to this path')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -171,8 +173,8 @@ def kernel_work(key):
         _, c, hw = key
         return 4.0 * c * hw + 8.0 * c * c, 2.0 * c * c * hw
     if k == 'gram_bwd_nhwc':
-        _, c, hw, acc = key
-        return (12.0 if acc else 8.0) * c * hw + 4.0 * c * c, 2.0 * c * c * hw
+        _, c, hw, mode = key                 # mode bit 0: accumulate (reads dF too); bit 1: fused ReLU backward
+        return (12.0 if (mode & 1) else 8.0) * c * hw + 4.0 * c * c, 2.0 * c * c * hw
     if k == 'bias_relu':
         return 8.0 * key[2], 0.0            # read + write the activation in place
     if k == 'relu_bwd':
@@ -186,6 +188,20 @@ def kernel_work(key):
     if k in ('chw_to_hwc', 'hwc_to_chw'):
         return 8.0 * key[1] * key[2], 0.0
     return 0.0, 0.0
+
+
+def ncu_traffic(kernel: str):
+    """DRAM bytes (read + write) of one launch of `kernel` from the committed `ncu --set full` capture of
+    tests/tools/ncu_target.py (profiles/r01_ncu_traffic.json; same shapes as the L=3 top level at N=1), or None."""
+    p = os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')
+    try:
+        table = json.load(open(p))
+    except (OSError, ValueError):
+        return None
+    if kernel.startswith('gram_bwd_nhwc/'):          # the fused-ReLU modes (2, 3) move the same DRAM bytes as 0, 1
+        head, mode = kernel.rsplit('/', 1)
+        kernel = f'{head}/{int(mode) & 1}'
+    return table.get(kernel)
 
 
 def kernel_table(summary, pk):
@@ -242,6 +258,8 @@ def run_ours(args):
     assert _lib.load().ast_device_check() == 0, _lib.last_error()
     if args.precision:
         nst.PRECISION = args.precision
+    from artstyletransfer_b200 import feature_path
+    feature_path.CUDNN_BENCHMARK = not args.no_cudnn_autotune
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
         parallel.init_sharding()
@@ -287,6 +305,9 @@ def run_ours(args):
                 f.write(prof.key_averages().table(sort_by='cuda_time_total', row_limit=60, max_name_column_width=90))
         barrier()
     # ---- per-kernel pass: the same closure launched eagerly with CUDA events around every C-ABI call ---------
+    ops.STATS.reset(enabled=True, timing=False)
+    job.optimizer_step()              # first eager closure after the graph: allocator warm-up, not measured
+    barrier()
     ops.STATS.reset(enabled=True, timing=True)
     probe_steps = 3
     c0 = job.step
@@ -314,14 +335,19 @@ def run_ours(args):
         del job
         torch.cuda.empty_cache()
 
+        first_yield_s = [None]
+
         async def drive():
             drv = nst.NeuralStyleTransfer(dev, 'vgg19', style_levels, args.optimizer)
             n, t_start, last = 0, None, None
+            t_call = time.perf_counter()
             total = args.warmup + args.steps
             iters = total if args.optimizer == 'adam' else 2 * total
             async for img, step in drv.process(content_levels, init, 10.0, iters, *WEIGHTS, name):
                 n += 1
                 last = (img, step)
+                if n == 1:
+                    first_yield_s[0] = time.perf_counter() - t_call
                 if n == args.warmup:
                     barrier()
                     t_start = (time.perf_counter(), step)
@@ -338,7 +364,8 @@ def run_ours(args):
         e2e = {'value': (step1 - step0) / wall, 'unit': UNIT, 'h2d_bytes_per_step': 0,
                'd2h_bytes_per_step': int(img.nbytes), 'timed': 'wall clock around K optimizer steps incl. the per-step '
                'image yield (device->host); job inputs uploaded once at setup',
-               'setup_h2d_bytes': int(sum(a.nbytes for a in content_levels + style_levels) + init.nbytes)}
+               'setup_h2d_bytes': int(sum(a.nbytes for a in content_levels + style_levels) + init.nbytes),
+               'setup_plus_first_step_s': round(first_yield_s[0], 3) if first_yield_s[0] else None}
 
     if world > 1:
         # CUDA graphs hold captured NCCL kernels: release them before the communicator goes away
@@ -356,13 +383,15 @@ def run_ours(args):
     pk = peaks()
     table = kernel_table(summary, pk)
     top = table[0] if table else None
+    top_key = next((k for k in summary if '/'.join(str(x) for x in k) == top['kernel']), None) if top else None
     roofline = None
     if top:
         bound = top['bound']
         achieved = top['GBps'] if bound == 'hbm' else top['TFLOPs']
         peak = pk['hbm_gbs'] if bound == 'hbm' else TF32_TFLOPS_MEASURED
         roofline = {'kernel': top['kernel'], 'bound': bound, 'achieved': achieved, 'peak': peak,
-                    'unit': 'GB/s' if bound == 'hbm' else 'TFLOP/s', 'frac': round(achieved / peak, 3), 'traffic': None,
+                    'unit': 'GB/s' if bound == 'hbm' else 'TFLOP/s', 'frac': round(achieved / peak, 3),
+                    'traffic': ncu_traffic(top['kernel']), 'algorithmic_bytes': kernel_work(top_key)[0],
                     'peak_source': pk['source'] if bound == 'hbm' else 'cuBLAS TF32 8192^3 measured on this pool '
                     '(profiles/r01_peaks.json)', 'ms_avg': top['ms_avg'], 'calls_in_probe_pass': top['calls']}
     ours_ms = sum(r['ms_total'] for r in table)
@@ -386,7 +415,7 @@ def run_ours(args):
                    'levels': args.levels, 'image': [H, W], 'optimizer': args.optimizer,
                    'parallelism': f'rowband{world}' if world > 1 else 'single',
                    'cache': f'working set {mem_gb:.1f} GB per step >> {L2_BYTES / 1e6:.0f} MB L2 (no flush needed)',
-                   'closures_timed': closures, 'cuda_graph': graphed, 'gram_operands': args.precision or ops.DEFAULT_PRECISION,
+                   'closures_timed': closures, 'cuda_graph': graphed, 'cudnn_autotune': not args.no_cudnn_autotune, 'gram_operands': args.precision or ops.DEFAULT_PRECISION,
                    'vgg_convs': 'cuDNN via torch ops on channels_last tensors (out of scope)',
                    'kernel_table': 'separate eager pass of 3 steps, CUDA events around every launch of this library'},
         'clocks': clk, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,

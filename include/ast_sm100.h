@@ -94,8 +94,12 @@ int ast_gram_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, 
  * accumulate != 0 adds into dF with TMA reduce-add (the SM never reads dF). */
 int ast_gram_mse_fwd_nhwc(const float* F, int C, int64_t HW, float scale, const float* A, float* out,
                           float* loss, void* ws, size_t ws_bytes, int round_out, void* stream);
+/* relu_mask != 0 (both here and in ast_mse_bwd): F / X is the output of a ReLU and the gradient written is the one
+ * w.r.t. that ReLU's INPUT: dF = (accumulate ? dF + v : v) * (F > 0) — the tap's loss gradient, the running
+ * activation gradient and torch's threshold_backward in one pass over the tensor. */
 int ast_gram_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale,
-                      const float* gscale, float* dF, int accumulate, int d_prerounded, void* stream);
+                      const float* gscale, float* dF, int accumulate, int d_prerounded,
+                      int relu_mask, void* stream);
 
 /* ---- Content MSE (neural_style_transfer.py:95) ---------------------------------------------
  *   *loss = scale * sum((X - T)^2)      (scale = 1/n for MSELoss(reduction='mean'))
@@ -104,7 +108,7 @@ size_t ast_reduce_workspace_bytes(void);
 int ast_mse_fwd(const float* X, const float* T, int64_t n, float scale, float* loss, void* ws,
                 size_t ws_bytes, void* stream);
 int ast_mse_bwd(const float* X, const float* T, int64_t n, float scale, const float* gscale,
-                float* dX, int accumulate, void* stream);
+                float* dX, int accumulate, int relu_mask, void* stream);
 
 /* ---- Glue between the cuDNN convolutions of the VGG19 feature path (neural_nets.py:53-68) --------------
  * Activations are (H, W, C) row-major (torch channels_last), C % 4 == 0, 16-byte aligned.  The convolutions

@@ -55,7 +55,7 @@ def test_argument_validation_without_gpu(lib):
     rc = lib.ast_gram_mse_fwd(p, 64, 64, 64, 1.0, None, p, None, p, 16, 0, None)
     assert rc == -4
     with pytest.raises(RuntimeError, match='ast_mse_bwd failed'):
-        _lib.call('ast_mse_bwd', None, None, 1, 1.0, None, None, 0, None)
+        _lib.call('ast_mse_bwd', None, None, 1, 1.0, None, None, 0, 0, None)
 
 
 def test_cpu_tensors_fail_loudly(lib):

@@ -162,3 +162,34 @@ def test_adam_50_steps_psnr_vs_oracle_loop(seeded_vgg, lr, min_psnr):
         optim.step()
     want = O.unprepare_img(img.detach().cpu().numpy())
     assert O.psnr(got, want) >= min_psnr
+
+
+@pytest.mark.parametrize('opt', ['adam', 'lbfgs'])
+def test_cuda_graph_closure_matches_eager(seeded_vgg, opt):
+    """The closure replayed from a CUDA graph (captured after two eager closures) must drive the optimizer
+    exactly like the eagerly launched closure: same step counters, same losses, same images."""
+    from artstyletransfer_b200 import neural_style_transfer as nst
+    content, style = O.synthetic_images(64, 96, seed=2)
+    c_lv = [content, O.bicubic_resize_hwc(content, 48, 32).astype(np.float32)]
+    s_lv = [style, O.bicubic_resize_hwc(style, 48, 32).astype(np.float32)]
+    init = np.clip(content * 0.6 + np.random.default_rng(5).uniform(0, 1, size=content.shape) * 0.4, 0, 1).astype(np.float32)
+    old_det = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    out = {}
+    try:
+        for graph in (False, True):
+            nst.GRAPH_CLOSURE = graph
+            job = nst._Job(dev(), 'vgg19', s_lv, opt, c_lv, init, 1.0, *WEIGHTS, 'graph-test')
+            losses = []
+            for _ in range(6):
+                job.optimizer_step()
+                losses.append(float(job.closure()))          # extra evaluation: also exercises replay-after-step
+            assert (job._graph is not None) == graph
+            out[graph] = (job.step, losses, job.optimizing_img.detach().clone(), job.optimizing_img.grad.clone())
+    finally:
+        nst.GRAPH_CLOSURE = True
+        torch.backends.cudnn.deterministic = old_det
+    assert out[True][0] == out[False][0]
+    np.testing.assert_allclose(out[True][1], out[False][1], rtol=1e-6)
+    assert torch.equal(out[True][2], out[False][2])
+    assert torch.equal(out[True][3], out[False][3])

@@ -133,3 +133,36 @@ def test_prerounded_d_gives_bit_identical_backward(c, hw):
     ops.gram_finalize(raw, c, 1.0 / (c * hw), a, d2, l2, ops.reduce_workspace(dev()), round_out=True)
     assert torch.equal(d2.view(torch.int32) & 0x1fff, torch.zeros_like(d2, dtype=torch.int32))
     assert rel(d2.cpu().numpy(), d0.cpu().numpy()) < 1e-3
+
+
+@pytest.mark.parametrize('c,hw', [(64, 100), (64, 4096 + 37), (128, 5000), (256, 3000), (512, 1536)])
+@pytest.mark.parametrize('accumulate', [False, True])
+def test_gram_bwd_nhwc_fused_relu_backward(c, hw, accumulate):
+    """relu_mask: the kernel writes the gradient w.r.t. the ReLU's INPUT — bit-identical to the unfused sequence
+    (gram_bwd accumulate, then relu_bwd in place) because both add the same fp32 values in the same order."""
+    from artstyletransfer_b200 import ops
+    f = _feat(c, hw, 5 * c + hw)
+    d = torch.randn((c, c), device=dev()) * 1e-2
+    d = ((d + d.t()) / 2).contiguous()
+    base = torch.randn((hw, c), device=dev()) * 1e-3
+    g_fused = base.clone() if accumulate else torch.full((hw, c), float('nan'), device=dev())
+    ops.gram_bwd_nhwc(d, f, c, hw, 1.5, None, g_fused, accumulate, relu_mask=True)
+    g_ref = base.clone() if accumulate else torch.empty((hw, c), device=dev())
+    ops.gram_bwd_nhwc(d, f, c, hw, 1.5, None, g_ref, accumulate)
+    ops.relu_bwd_(g_ref, f)
+    assert not torch.isnan(g_fused).any()
+    assert torch.equal(g_fused, g_ref)
+    assert float(g_fused[f <= 0].abs().max()) == 0.0
+
+
+def test_mse_bwd_fused_relu_backward():
+    from artstyletransfer_b200 import ops
+    n = 512 * 33 * 7 + 3
+    x = torch.relu(torch.randn(n, device=dev())); t = torch.randn(n, device=dev())
+    base = torch.randn(n, device=dev())
+    for acc in (False, True):
+        a = base.clone(); b = base.clone()
+        ops.mse_bwd(x, t, 0.25, None, a, acc, True)
+        ops.mse_bwd(x, t, 0.25, None, b, acc, False)
+        b = torch.where(x > 0, b, torch.zeros_like(b))
+        assert torch.equal(a, b)

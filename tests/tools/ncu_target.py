@@ -1,7 +1,7 @@
 """Small target for `ncu --set full`: ONE launch of each hot kernel of the channels-last path at the L=3 top-level
 sizes (after one untimed warm-up launch each, which ncu skips with -s): the (HW, C) Gram forward / backward for the
 four VGG widths, the glue kernels on the largest activations, the content MSE, TV and the bicubic pyramid step.
-usage: python tests/tools/ncu_target.py [warm]   ('warm' = also do the warm-up launches, for a plain run)"""
+usage: python tests/tools/ncu_target.py [gram] [glue] [elementwise]   (default: all groups)"""
 import os
 import sys
 
@@ -21,7 +21,8 @@ def once(fn):
     fn()
 
 
-for c, hw in [(64, 6291456), (128, 1572864), (256, 393216), (512, 98304)]:
+GROUPS = set(sys.argv[1:]) or {'gram', 'glue', 'elementwise'}
+for c, hw in ([(64, 6291456), (128, 1572864), (256, 393216), (512, 98304)] if 'gram' in GROUPS else []):
     f = torch.relu(torch.randn((hw, c), device=dev)) * 0.25
     a = torch.rand((c, c), device=dev) * 1e-3
     d = torch.empty((c, c), device=dev); loss = torch.empty((), device=dev); df = torch.zeros_like(f)
@@ -33,6 +34,8 @@ for c, hw in [(64, 6291456), (128, 1572864), (256, 393216), (512, 98304)]:
     print(c, hw, float(loss))
     del f, df
 
+if 'glue' not in GROUPS and 'elementwise' not in GROUPS:
+    sys.exit(0)
 # glue on relu1_x-sized activations (64 x 2048 x 3072 = 1.6 GB) and the pool after them
 y = torch.randn((1, 64, 2048, 3072), device=dev).contiguous(memory_format=CL)
 b = torch.randn(64, device=dev)

@@ -24,6 +24,7 @@ for c, hw in ((64, 6291456), (128, 1572864), (256, 393216), (512, 98304), (64, 1
     ops.gram_mse_fwd_nhwc(f, c, hw, 1.0 / (c * hw), a, dr, loss, ws, round_out=True)
     t6 = timeit(lambda: ops.gram_bwd_nhwc(dr, f, c, hw, 1e-3, None, df, False, d_prerounded=True), flush, iters=7)
     t7 = timeit(lambda: ops.gram_bwd_nhwc(dr, f, c, hw, 1e-3, None, df, True, d_prerounded=True), flush, iters=7)
+    t8 = timeit(lambda: ops.gram_bwd_nhwc(dr, f, c, hw, 1e-3, None, df, True, d_prerounded=True, relu_mask=True), flush, iters=7)
     t4 = timeit(lambda: ops.gram_mse_fwd(fn, c, hw, 1.0 / (c * hw), a, d, loss, ws, 0), flush, iters=7)
     t5 = timeit(lambda: ops.gram_bwd(d, fn, c, hw, 1e-3, None, dfn, False, 0), flush, iters=7)
     print(json.dumps({'C': c, 'HW': hw, 'noround': os.environ.get('AST_GRAM_FWD_NOROUND'),
@@ -32,5 +33,6 @@ for c, hw in ((64, 6291456), (128, 1572864), (256, 393216), (512, 98304), (64, 1
                       'nhwc_bwd_acc_ms': round(t3, 4), 'nhwc_bwd_acc_GBps': round((byb + 4.0 * c * hw) / t3 / 1e6),
                       'nhwc_bwd_prer_ms': round(t6, 4), 'nhwc_bwd_prer_GBps': round(byb / t6 / 1e6), 'nhwc_bwd_prer_TF': round(fl / t6 / 1e9),
                       'nhwc_bwd_prer_acc_ms': round(t7, 4), 'nhwc_bwd_prer_acc_GBps': round((byb + 4.0 * c * hw) / t7 / 1e6),
+                      'nhwc_bwd_acc_relu_ms': round(t8, 4), 'nhwc_bwd_acc_relu_GBps': round((byb + 4.0 * c * hw) / t8 / 1e6),
                       'nchw_fwd_ms': round(t4, 4), 'nchw_fwd_GBps': round(byf / t4 / 1e6),
                       'nchw_bwd_ms': round(t5, 4), 'nchw_bwd_GBps': round(byb / t5 / 1e6)}), flush=True)
