@@ -351,7 +351,7 @@ def mse_fwd(x, t, scale, loss, ws):
 
 
 def mse_bwd(x, t, scale, gscale, dx, accumulate, relu_mask=False):
-    _launch(x.device, ('mse_bwd', x.numel()), 'ast_mse_bwd', x.data_ptr(), t.data_ptr(), x.numel(), scale,
+    _launch(x.device, ('mse_bwd', x.numel(), int(bool(accumulate))), 'ast_mse_bwd', x.data_ptr(), t.data_ptr(), x.numel(), scale,
             gscale.data_ptr() if gscale is not None else None, dx.data_ptr(), int(accumulate), int(relu_mask))
 
 

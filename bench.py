@@ -161,7 +161,7 @@ def kernel_work(key):
     if k == 'mse_fwd':
         return 8.0 * key[1], 0.0
     if k == 'mse_bwd':
-        return 12.0 * key[1], 0.0
+        return (16.0 if (len(key) > 2 and key[2]) else 12.0) * key[1], 0.0   # X, T (, dX) read; dX written
     if k == 'tv_fwd':
         return 4.0 * key[1], 0.0
     if k == 'tv_bwd':
@@ -198,6 +198,8 @@ def ncu_traffic(kernel: str):
         table = json.load(open(p))
     except (OSError, ValueError):
         return None
+    if kernel.startswith('mse_bwd/') and kernel.count('/') == 2:
+        kernel = kernel.rsplit('/', 1)[0]            # captured in accumulate mode
     if kernel.startswith('gram_bwd_nhwc/'):          # the fused-ReLU modes (2, 3) move the same DRAM bytes as 0, 1
         head, mode = kernel.rsplit('/', 1)
         kernel = f'{head}/{int(mode) & 1}'
