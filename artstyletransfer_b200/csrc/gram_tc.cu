@@ -565,20 +565,25 @@ struct BwdNhwcCfg {
   static constexpr int kFBytes = 128 * ROW_BYTES;                       // 16 KB: 128 positions x 32 channels
   static constexpr int kDChunkBytes = C * ROW_BYTES;                    // C rows x 32 k
   static constexpr int kStageBytes = kFBytes + (kResidentD ? 0 : kDChunkBytes);
-  static constexpr int kStages = (C == 512) ? 2 : (C == 256 ? 4 : 6);
+  static constexpr int kStages = (C == 512) ? 2 : ((C == 256 || C == 128) ? 4 : 6);
   static constexpr int kDResBytes = kResidentD ? C * C * 4 : 0;
   static constexpr int kAccBufs = (C == 512) ? 1 : 2;
   static constexpr int kTmemCols = (C == 64) ? 128 : (C == 128 ? 256 : 512);
   static constexpr int kUmmaN = (C <= 256) ? C : 256;
   static constexpr int kDBoxRows = (C <= 256) ? C : 256;
-  static constexpr int kOutBytes = 4 * 2 * 4096;                        // per epilogue warp: two 32 x 32 fp32 blocks
+  // epilogue groups of 4 warps (one warp per TMEM sub-partition); group e takes the 32-column groups g with
+  // g % kEpiGroups == e.  Two groups where the epilogue also reads global memory (fused ReLU backward): the loads
+  // in flight per SM, not the sectors per request, bound that path.
+  static constexpr int kEpiGroups = (C == 256) ? 1 : 2;   // measured: C = 256 is faster with 4 stages + 1 group
+  static constexpr int kThreads = 192 + 128 * kEpiGroups;
+  static constexpr int kOutBytes = 4 * kEpiGroups * 2 * 4096;           // per epilogue warp: two 32 x 32 fp32 blocks
   static constexpr int kSmemBytes = kStages * kStageBytes + kDResBytes + kOutBytes + 1024 + 256;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
-// warp 0: TMA loads, warp 1: MMA + TMEM, warps 2..5: converters, warps 6..9: epilogue + TMA stores.
+// warp 0: TMA loads, warp 1: MMA + TMEM, warps 2..5: converters, warps 6..: epilogue groups + TMA stores.
 template <int C>
-__global__ void __launch_bounds__(320, 1) gram_bwd_nhwc_tc_kernel(const __grid_constant__ CUtensorMap tmapF,
+__global__ void __launch_bounds__(BwdNhwcCfg<C>::kThreads, 1) gram_bwd_nhwc_tc_kernel(const __grid_constant__ CUtensorMap tmapF,
                                                                  const __grid_constant__ CUtensorMap tmapD,
                                                                  const __grid_constant__ CUtensorMap tmapO,
                                                                  const __grid_constant__ BwdNhwcParams P) {
@@ -610,7 +615,7 @@ __global__ void __launch_bounds__(320, 1) gram_bwd_nhwc_tc_kernel(const __grid_c
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_accf + 8 * b, 1);
-      mbar_init(bar_acce + 8 * b, 128);
+      mbar_init(bar_acce + 8 * b, 128 * Cfg::kEpiGroups);
     }
     mbar_init(bar_dfull, 1);
     mbar_init(bar_dconv, 128);
@@ -710,6 +715,7 @@ __global__ void __launch_bounds__(320, 1) gram_bwd_nhwc_tc_kernel(const __grid_c
     const uint32_t lane_addr = tmem_base + ((uint32_t)(sub * 32) << 16);
     const float scale = P.gscale ? P.scale * __ldg(P.gscale) : P.scale;
     const uint32_t stg = smem_u32(ostage + (warp - 6) * 8192);
+    const int egrp = (warp - 6) >> 2;
     const uint32_t row_off = (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
     uint32_t v[32];
@@ -721,7 +727,7 @@ __global__ void __launch_bounds__(320, 1) gram_bwd_nhwc_tc_kernel(const __grid_c
       mbar_wait(bar_accf + 8 * b, bph);
       tc_fence_after();
 #pragma unroll 1
-      for (int g = 0; g < C / 32; ++g) {
+      for (int g = egrp; g < C / 32; g += Cfg::kEpiGroups) {
         tmem_ld_x32(lane_addr + b * C + g * 32, v);
         tmem_ld_wait();
         float o[32];
@@ -779,6 +785,199 @@ __global__ void __launch_bounds__(320, 1) gram_bwd_nhwc_tc_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward, (HW, C) layout, C = 512: CTA pair (cta_group::2)
+// ------------------------------------------------------------------------------------------------------
+// The one-CTA kernel above is shared-memory-bandwidth bound at C = 512: per 32-channel K chunk a CTA writes 80 KB
+// (F 16 + D 64), its tensor core reads 96 KB (A 4 + B 8 KB per MMA) and the epilogue moves 32 KB, for 1024 cycles of
+// MMA.  A pair of CTAs (two SMs of a TPC) computes M = 256 positions per MMA: each CTA keeps its own 128 positions
+// of F and only HALF of the B operand (128 of the 256 output channels of each N block), so per CTA the D traffic
+// halves (TMA 48 KB, tensor-core reads 64 KB per chunk) and four stages fit where two did.
+// Protocol (s = stage): each CTA's TMA fills its full[s]; its converters round the F part and arrive on the
+// LEADER's conv[s] (count 256, the peer's through shared::cluster); the leader's MMA thread issues
+// tcgen05.mma.cta_group::2 and commits with a multicast arrive on empty[s] of BOTH CTAs; the accumulator-full
+// commit is multicast too; both CTAs' epilogue warps arrive on the leader's acc_empty.
+struct Bwd2CtaCfg {
+  static constexpr int C = 512;
+  static constexpr int kFBytes = 128 * ROW_BYTES;                 // 16 KB: this CTA's 128 positions x 32 channels
+  static constexpr int kDHalfBytes = 128 * ROW_BYTES;             // 16 KB: 128 output channels x 32 k
+  static constexpr int kStageBytes = kFBytes + 2 * kDHalfBytes;   // 48 KB
+  static constexpr int kStages = 4;
+  static constexpr int kOutBytes = 4 * 2 * 4096;
+  static constexpr int kThreads = 320;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + 256;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+gram_bwd_nhwc_2cta_kernel(const __grid_constant__ CUtensorMap tmapF, const __grid_constant__ CUtensorMap tmapD,
+                          const __grid_constant__ CUtensorMap tmapO, const __grid_constant__ BwdNhwcParams P) {
+  using Cfg = Bwd2CtaCfg;
+  constexpr int C = 512, S = Cfg::kStages, KC = C / BK;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ostage = smem + S * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + Cfg::kOutBytes);
+  // full[S] conv[S] empty[S] acc_full acc_empty
+  const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + S), bar_empty = smem_u32(bars + 2 * S),
+                 bar_accf = smem_u32(bars + 3 * S), bar_acce = smem_u32(bars + 3 * S + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int my_tiles = (pair < P.n_tiles) ? (P.n_tiles - 1 - pair) / n_pairs + 1 : 0;   // P.n_tiles: 256-position tiles
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmapF);
+    prefetch_tmap(&tmapD);
+    prefetch_tmap(&tmapO);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, 256);     // both CTAs' converters (only the leader's copy is used)
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_accf, 1);
+    mbar_init(bar_acce, 256);               // both CTAs' epilogue warps (leader's copy)
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(smem_u32(tmem_slot), 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();                       // barrier inits + TMEM allocation visible in both CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (each CTA: its 128 positions of F, its half of both N blocks of D) =====
+      int it = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int64_t n0 = ((int64_t)pair + (int64_t)ti * n_pairs) * 256 + rank * 128;
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)Cfg::kStageBytes);
+          const uint32_t dst = smem_u32(smem + s * Cfg::kStageBytes);
+          tma_load_2d(dst, &tmapF, bar_full + 8 * s, kc * BK, (int)n0);
+          tma_load_2d(dst + Cfg::kFBytes, &tmapD, bar_full + 8 * s, kc * BK, (int)(rank * 128));
+          tma_load_2d(dst + Cfg::kFBytes + Cfg::kDHalfBytes, &tmapD, bar_full + 8 * s, kc * BK, (int)(256 + rank * 128));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t idesc = umma_idesc_tf32(256, 256, 0, 0);
+      int it = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        mbar_wait(bar_acce, ((uint32_t)ti & 1u) ^ 1u);    // both epilogues have drained the accumulator
+        tc_fence_after();
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(bar_conv + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t f_base = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t d_base = f_base + Cfg::kFBytes;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint32_t acc = (kc > 0 || k > 0) ? 1u : 0u;
+            const uint64_t ad = umma_desc_sw128(f_base + k * 32, 16, 1024);
+            umma_tf32_2cta(tmem_base, ad, umma_desc_sw128(d_base + k * 32, 16, 1024), idesc, acc);
+            umma_tf32_2cta(tmem_base + 256, ad, umma_desc_sw128(d_base + Cfg::kDHalfBytes + k * 32, 16, 1024), idesc, acc);
+          }
+          umma_commit_2cta(bar_empty + 8 * s, 3);
+        }
+        umma_commit_2cta(bar_accf, 3);
+      }
+    }
+  } else if (warp < 6) {
+    // ===== converters: round this CTA's F tile, then tell the leader's MMA thread =====
+    const int ctid = threadIdx.x - 64;
+    const int total = my_tiles * KC;
+    const uint32_t conv0 = mapa_shared(bar_conv, 0);
+    for (int it = 0; it < total; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (uint32_t)(it / S) & 1u;
+      mbar_wait(bar_full + 8 * s, ph);
+      convert_tf32_inplace(smem + s * Cfg::kStageBytes, P.d_prerounded ? Cfg::kFBytes : Cfg::kStageBytes, ctid);
+      fence_proxy_async_smem();
+      mbar_arrive_cluster(conv0 + 8 * s);
+    }
+  } else {
+    // ===== epilogue (each CTA: its own 128 positions = its own TMEM lanes) =====
+    const int sub = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(sub * 32) << 16);
+    const float scale = P.gscale ? P.scale * __ldg(P.gscale) : P.scale;
+    const uint32_t stg = smem_u32(ostage + (warp - 6) * 8192);
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const uint32_t acce0 = mapa_shared(bar_acce, 0);
+    uint32_t v[32];
+    uint32_t nbuf = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int64_t p0 = ((int64_t)pair + (int64_t)ti * n_pairs) * 256 + rank * 128 + sub * 32;
+      mbar_wait(bar_accf, (uint32_t)ti & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < C / 32; ++g) {
+        tmem_ld_x32(lane_addr + g * 32, v);
+        tmem_ld_wait();
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = scale * __uint_as_float(v[j]);
+        if (P.relu_mask) {
+          const int64_t p = p0 + lane;
+          if (p < P.HW) {
+            const float4* fr = reinterpret_cast<const float4*>(P.F + p * C + g * 32);
+            const float4* gr = reinterpret_cast<const float4*>(P.dF + p * C + g * 32);
+            float4 f[8], q[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[j] = __ldg(fr + j);
+              q[j] = P.accumulate ? gr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              o[4 * j] = f[j].x > 0.f ? o[4 * j] + q[j].x : 0.f;
+              o[4 * j + 1] = f[j].y > 0.f ? o[4 * j + 1] + q[j].y : 0.f;
+              o[4 * j + 2] = f[j].z > 0.f ? o[4 * j + 2] + q[j].z : 0.f;
+              o[4 * j + 3] = f[j].w > 0.f ? o[4 * j + 3] + q[j].w : 0.f;
+            }
+          }
+        }
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        const uint32_t buf = stg + (nbuf & 1u) * 4096u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = buf + row_off + ((((uint32_t)j) ^ sw) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[4 * j]), "f"(o[4 * j + 1]),
+                       "f"(o[4 * j + 2]), "f"(o[4 * j + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && p0 < P.HW) {
+          if (P.accumulate && !P.relu_mask) tma_reduce_add_2d(&tmapO, buf, g * 32, (int)p0);
+          else tma_store_2d(&tmapO, buf, g * 32, (int)p0);
+          tma_store_commit();
+        }
+        ++nbuf;
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(acce0);
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  cluster_sync_all();                       // nobody may still be using the pair's TMEM / shared memory
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -973,8 +1172,43 @@ static int launch_bwd_nhwc(const float* D, const float* F, int64_t HW, float sca
     return AST_ERR_CUDA;
   }
   const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
-  gram_bwd_nhwc_tc_kernel<C><<<grid, 320, Cfg::kSmemBytes, stream>>>(tmF, tmD, tmO, P);
+  gram_bwd_nhwc_tc_kernel<C><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmF, tmD, tmO, P);
   return check_launch("gram_bwd_nhwc_tc");
+}
+
+static int launch_bwd_nhwc_2cta(const float* D, const float* F, int64_t HW, float scale, const float* gscale, float* dF,
+                                int accumulate, int d_prerounded, int relu_mask, int num_sms, cudaStream_t stream) {
+  using Cfg = Bwd2CtaCfg;
+  constexpr int C = 512;
+  CUtensorMap tmF, tmD, tmO;
+  int rc = make_tmap(&tmF, F, (uint64_t)HW, C, C, 128);
+  if (rc != AST_OK) return rc;
+  rc = make_tmap(&tmD, D, C, C, C, 128);
+  if (rc != AST_OK) return rc;
+  rc = make_tmap(&tmO, dF, (uint64_t)HW, C, C, 32);
+  if (rc != AST_OK) return rc;
+  BwdNhwcParams P;
+  P.HW = HW;
+  P.n_tiles = (int)((HW + 255) / 256);      // 256-position tiles, one per CTA pair
+  P.scale = scale;
+  P.gscale = gscale;
+  P.accumulate = accumulate;
+  P.d_prerounded = d_prerounded;
+  P.relu_mask = relu_mask;
+  P.F = F;
+  P.dF = dF;
+  P.C = C;
+  cudaError_t e = cudaFuncSetAttribute(gram_bwd_nhwc_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes);
+  if (e != cudaSuccess) {
+    set_error("gram_tc_bwd_nhwc(2cta): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return AST_ERR_CUDA;
+  }
+  int pairs = num_sms / 2;
+  if (pairs > P.n_tiles) pairs = P.n_tiles;
+  if (pairs < 1) pairs = 1;
+  gram_bwd_nhwc_2cta_kernel<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmF, tmD, tmO, P);
+  return check_launch("gram_bwd_nhwc_2cta");
 }
 
 int gram_tc_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale, float* dF,
@@ -983,7 +1217,13 @@ int gram_tc_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float sc
     case 64: return launch_bwd_nhwc<64>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
     case 128: return launch_bwd_nhwc<128>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
     case 256: return launch_bwd_nhwc<256>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
-    case 512: return launch_bwd_nhwc<512>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
+    case 512: {
+      // CTA-pair kernel by default; AST_GRAM_BWD_2CTA=0 selects the one-CTA kernel (comparison / fallback)
+      static const int use_pair = (getenv("AST_GRAM_BWD_2CTA") && atoi(getenv("AST_GRAM_BWD_2CTA")) == 0) ? 0 : 1;
+      if (use_pair)
+        return launch_bwd_nhwc_2cta(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
+      return launch_bwd_nhwc<512>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
+    }
   }
   set_error("gram_tc_bwd_nhwc: unsupported C=%d", C);
   return AST_ERR_UNSUPPORTED;
