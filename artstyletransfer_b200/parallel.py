@@ -57,6 +57,130 @@ class BandPlan:
         return self.r0 // stride, self.r1 // stride
 
 
+BAND_OVERHEAD = float(os.environ.get('AST_BAND_OVERHEAD', '0.03'))
+MIN_BAND_ROWS = 2 * ALIGN
+
+
+class PyramidBands:
+    """Pure host logic: which rows of WHICH LEVEL every rank owns (the level-aware successor of BandPlan).
+
+    Cutting every level into `world` equal bands makes the small levels tiny (a 32-row band of the 256x384 level is
+    a handful of CTAs per launch) and multiplies the number of latency-sized launches per rank by the number of
+    levels.  The levels' costs are 64 : 16 : 4 : 1, so instead the ranks are filled like a snake: rank 0 takes rows
+    of the top level until its share of the whole pyramid's cost is reached, the next rank continues where it
+    stopped, and whoever finishes a level carries on with the level below.  At 8 ranks and 4 levels that puts the
+    2048x3072 level on ranks 0-5 and the three lower levels on the remaining ranks; most ranks run ONE band.
+
+    Cost model (units: the whole top level = 1): rows * width / (H0 * W0) per band plus `overhead` per band (the
+    ~120 launches of a band cost their latency however few rows it has).  The per-rank budget T is scanned and the
+    plan with the smallest maximum load wins.  Band edges are multiples of 16 rows (the four 2x2 max-pools never
+    straddle ranks), bands are at least 32 rows; bounds[level] is the non-decreasing list of world + 1 row edges,
+    an empty band (two equal edges) means the rank does not work on that level."""
+
+    def __init__(self, sizes: Sequence[Sequence[int]], world: int, overhead: Optional[float] = None,
+                 uniform: bool = False):
+        self.sizes = [(int(h), int(w)) for h, w in sizes]
+        self.world = int(world)
+        self.overhead = BAND_OVERHEAD if overhead is None else float(overhead)
+        for h, w in self.sizes:
+            if h % ALIGN or h < MIN_BAND_ROWS:
+                raise ValueError(f'level height {h} is not a multiple of {ALIGN} rows >= {MIN_BAND_ROWS}')
+        if uniform:
+            if not all(BandPlan.shardable(h, world) for h, _ in self.sizes):
+                raise ValueError(f'levels {self.sizes} cannot all be cut into {world} equal bands')
+            self.bounds = [[r * (h // world) for r in range(world + 1)] for h, _ in self.sizes]
+        else:
+            self.bounds = self._search()
+
+    # -- planning -------------------------------------------------------------------------------------------
+    def _unit(self):
+        return float(self.sizes[0][0] * self.sizes[0][1])
+
+    def _snake(self, budget: float):
+        world, ov = self.world, self.overhead
+        rank, load = 0, 0.0
+        bounds = []
+        for h, w in self.sizes:
+            per_row = w / self._unit()
+            rows_of = [0] * world
+            row = 0
+            while row < h:
+                remaining = h - row
+                if rank == world - 1:
+                    take = remaining
+                else:
+                    cap = int(max(budget - load - ov, 0.0) / per_row) // ALIGN * ALIGN
+                    if cap >= remaining:
+                        take = remaining
+                    elif cap < MIN_BAND_ROWS:
+                        if load > 0.0:                 # no room left for a worthwhile band: the next rank goes on
+                            rank, load = rank + 1, 0.0
+                            continue
+                        take = min(remaining, MIN_BAND_ROWS)
+                    else:
+                        take = cap
+                    if 0 < remaining - take < MIN_BAND_ROWS:      # never leave a sliver behind
+                        take = remaining - MIN_BAND_ROWS if remaining - MIN_BAND_ROWS >= MIN_BAND_ROWS else remaining
+                rows_of[rank] += take
+                load += take * per_row + ov
+                row += take
+                if row < h:                            # this rank is full; the level continues on the next one
+                    rank, load = rank + 1, 0.0
+            edges = [0]
+            for r in range(world):
+                edges.append(edges[-1] + rows_of[r])
+            bounds.append(edges)
+        return bounds
+
+    def loads(self, bounds=None):
+        """Modelled cost per rank (top level = 1)."""
+        bounds = self.bounds if bounds is None else bounds
+        out = [0.0] * self.world
+        for (h, w), edges in zip(self.sizes, bounds):
+            for r in range(self.world):
+                rows = edges[r + 1] - edges[r]
+                if rows:
+                    out[r] += rows * w / self._unit() + self.overhead
+        return out
+
+    def _search(self):
+        work = sum(h * w for h, w in self.sizes) / self._unit()
+        lo = work / self.world
+        hi = work + self.overhead * len(self.sizes)
+        best = None
+        steps = 400
+        for i in range(steps + 1):
+            budget = lo * (hi / lo) ** (i / steps) if hi > lo else lo
+            bounds = self._snake(budget)
+            n_bands = sum(1 for edges in bounds for r in range(self.world) if edges[r + 1] > edges[r])
+            key = (round(max(self.loads(bounds)), 9), n_bands)
+            if best is None or key < best[0]:
+                best = (key, bounds)
+        return best[1]
+
+    # -- queries --------------------------------------------------------------------------------------------
+    def band(self, level: int, rank: int):
+        """(first owned row, one past the last owned row) of `rank` at `level`; equal when it owns nothing."""
+        return self.bounds[level][rank], self.bounds[level][rank + 1]
+
+    def neighbours(self, level: int, rank: int):
+        """(rank owning the rows above this rank's band, rank owning the rows below), None at the image border or
+        when this rank has no band at the level."""
+        edges = self.bounds[level]
+        if edges[rank + 1] == edges[rank]:
+            return None, None
+        up = next((r for r in range(rank - 1, -1, -1) if edges[r + 1] > edges[r]), None)
+        dn = next((r for r in range(rank + 1, self.world) if edges[r + 1] > edges[r]), None)
+        return up, dn
+
+    def describe(self) -> str:
+        parts = []
+        for li, ((h, w), edges) in enumerate(zip(self.sizes, self.bounds)):
+            owners = [f'r{r}:{edges[r + 1] - edges[r]}' for r in range(self.world) if edges[r + 1] > edges[r]]
+            parts.append(f'{h}x{w}[' + ' '.join(owners) + ']')
+        return ' '.join(parts)
+
+
 def pack_layout(channels: Sequence[int]):
     """Offsets of the raw Grams in the all-reduced buffer; the content SSE sits in the last slot."""
     offs, o = [], 0
@@ -89,8 +213,11 @@ class TorchDistGroup:
 
 def halo_exchange(group, rows, zero_border: bool = False) -> None:
     """rows: one (h + 2, w, C) contiguous view of a padded band, or a list of them (row 0 and row h+1 are the
-    halos).  Sends the first / last owned row of every band to the rank above / below and receives their edge rows
-    into the halos, all in ONE grouped exchange.
+    halos); a list entry may also be (view, up, dn) naming the ranks that own the rows above / below this band
+    (None at the image border) — the default is rank - 1 / rank + 1, the plan of equal bands.  Sends the first /
+    last owned row of every band to its neighbours and receives their edge rows into the halos, all in ONE grouped
+    exchange (called with an empty list by a rank that has no band at this step, so emulated collectives stay in
+    step; over NCCL that is a no-op).
 
     Forward (activations, zero_border=False): halos at the image border are left alone — they hold the
     convolution's zero padding and nothing ever writes them.
@@ -99,16 +226,21 @@ def halo_exchange(group, rows, zero_border: bool = False) -> None:
     row outside the image, so a border halo is zeroed (gradient buffers are recycled, unlike activation bands)."""
     if torch.is_tensor(rows):
         rows = [rows]
-    up, dn = group.rank - 1, group.rank + 1
     sends, recvs = [], []
-    for r in rows:
+    for entry in rows:
+        if torch.is_tensor(entry):
+            r = entry
+            up = group.rank - 1 if group.rank > 0 else None
+            dn = group.rank + 1 if group.rank + 1 < group.world else None
+        else:
+            r, up, dn = entry
         h = r.shape[0] - 2
-        if up >= 0:
+        if up is not None:
             sends.append((r[1], up))
             recvs.append((r[0], up))
         elif zero_border:
             r[0].zero_()
-        if dn < group.world:
+        if dn is not None:
             sends.append((r[h], dn))
             recvs.append((r[h + 1], dn))
         elif zero_border:
@@ -263,20 +395,44 @@ class ShardLevelLossFn(torch.autograd.Function):
         return (None, d_img, d_content, *d_style)
 
 
+PLAN = None       # the PyramidBands of the most recent maybe_shard() (None: equal bands or nothing sharded)
+
+
 def maybe_shard(loss_builders, optimizing_img, neural_net, content_idx, style_idx, weights) -> int:
     """Hook called by NeuralStyleTransfer.process after the per-level LossBuilders exist.  Returns the number of
-    levels that were sharded (0 on the single-process path)."""
+    levels that were sharded (0 on the single-process path).
+
+    When every level can take the halo-exchange path the rows of the WHOLE pyramid are dealt out by PyramidBands
+    (level-aware: a rank owns rows of one or two levels, AST_BANDS=uniform restores equal bands of every level);
+    otherwise each shardable level is cut into `world` equal bands as before."""
+    global PLAN
+    PLAN = None
     if _GROUP is None or _GROUP.world == 1 and os.environ.get('AST_SHARD_SINGLE', '0') != '1':
         return 0
     from . import ops, neural_style_transfer as nst
+    from .sharded_path import ShardedPathLevel
     h, w = optimizing_img.shape[-2], optimizing_img.shape[-1]
+    rank, world_ = _GROUP.rank, _GROUP.world
+    sizes = [(h >> i, w >> i) for i in range(len(loss_builders))]
+    plans = [lb.path_plan(optimizing_img) for lb in loss_builders]
+    uniform = os.environ.get('AST_BANDS', 'pyramid') == 'uniform'
+    whole = all(p is not None for p in plans) and all(
+        lh % ALIGN == 0 and lw % ALIGN == 0 and lh >= MIN_BAND_ROWS and h % (1 << i) == 0 and w % (1 << i) == 0
+        for i, (lh, lw) in enumerate(sizes))
+    if whole and not (uniform and not all(BandPlan.shardable(lh, world_) for lh, _ in sizes)):
+        PLAN = PyramidBands(sizes, world_, uniform=uniform)
+        for i, lb in enumerate(loss_builders):
+            r0, r1 = PLAN.band(i, rank)
+            up, dn = PLAN.neighbours(i, rank)
+            lb.shard = ShardedPathLevel(_GROUP, plans[i], lb.target_images[0], lb.target_images[1], content_idx,
+                                        style_idx, weights, sizes[i][0], sizes[i][1], band=(r0, r1, up, dn))
+        return len(loss_builders)
     n = 0
     for i, lb in enumerate(loss_builders):
-        lh, lw = h >> i, w >> i
-        ok = BandPlan.shardable(lh, _GROUP.world) and lw % ALIGN == 0 and (h % (1 << i) == 0)
-        plan = lb.path_plan(optimizing_img) if ok else None
+        lh, lw = sizes[i]
+        ok = BandPlan.shardable(lh, world_) and lw % ALIGN == 0 and (h % (1 << i) == 0)
+        plan = plans[i] if ok else None
         if plan is not None:
-            from .sharded_path import ShardedPathLevel
             lb.shard = ShardedPathLevel(_GROUP, plan, lb.target_images[0], lb.target_images[1], content_idx,
                                         style_idx, weights, lh, lw)
             n += 1

@@ -76,29 +76,42 @@ class ShardedPathLevel:
     """Replaces LossBuilder.build for one level when sharding is on (same return contract)."""
 
     def __init__(self, group, plan: fp.FeaturePlan, content_img: torch.Tensor, style_img: torch.Tensor,
-                 content_idx: int, style_idx: Sequence[int], weights, height: int, width: int):
+                 content_idx: int, style_idx: Sequence[int], weights, height: int, width: int, band=None):
+        """band: (r0, r1, up, dn) from parallel.PyramidBands — the owned rows and the ranks holding the rows above /
+        below (None at the image border); r0 == r1 when this rank does not work on the level (it still joins the
+        all-reduce and finalises the loss).  Default: `world` equal bands, neighbours rank -+ 1."""
         self.group, self.plan = group, plan
         self.cidx, self.sidx = content_idx, list(style_idx)
         self.weights = tuple(float(w) for w in weights)
         self.H, self.W = height, width
-        self.band = par.BandPlan(height, group.rank, group.world, halo=0)
-        self.hb = self.band.r1 - self.band.r0
-        dev = content_img.device
+        if band is None:
+            bp = par.BandPlan(height, group.rank, group.world, halo=0)
+            band = (bp.r0, bp.r1, group.rank - 1 if group.rank > 0 else None,
+                    group.rank + 1 if group.rank + 1 < group.world else None)
+        self.r0, self.r1, self.up, self.dn = band
+        self.hb = self.r1 - self.r0
+        if self.hb and (self.r0 % par.ALIGN or self.r1 % par.ALIGN or not 0 <= self.r0 < self.r1 <= height):
+            raise ValueError(f'band rows [{self.r0}, {self.r1}) of a {height}-row level must be multiples of {par.ALIGN}')
+        dev = self.device = content_img.device
         self.wss = ops.LevelWorkspaces()
         # targets: every rank runs the whole content / style image once at set-up (replicated, not on the hot path)
         tg = fp.build_targets(plan, content_img, style_img, content_idx, style_idx, self.wss)
         self.target_grams = tg.grams
         cs = par.LAYER_STRIDE[content_idx]
         crow = _rows(tg.content_cl)
-        self.target_content_band = crow[self.band.r0 // cs:self.band.r1 // cs].contiguous()
+        self.target_content_band = crow[self.r0 // cs:self.r1 // cs].contiguous()
         self.content_numel_global = tg.content_cl.numel()
         self.channels = [g.shape[-1] for g in tg.grams]
         self.offs, self.content_slot, self.n_packed = par.pack_layout(self.channels)
         self.fin_ws = [ops.reduce_workspace(dev) for _ in self.sidx]
+        self.generation = 0
+        self.bufs: List[torch.Tensor] = []
+        if not self.hb:
+            self.xin = None
+            return
         # persistent padded activation bands: xin (the image band) and one per step
         c0 = plan.steps[0][3]
         self.xin = torch.empty((1, c0, self.hb + 2, width), dtype=torch.float32, device=dev, memory_format=_CL).zero_()
-        self.bufs: List[torch.Tensor] = []
         c, h, w = c0, self.hb, width
         for sidx in range(plan.n_steps_needed):
             st = plan.steps[sidx]
@@ -107,7 +120,6 @@ class ShardedPathLevel:
             else:
                 h, w = h // 2, w // 2
             self.bufs.append(torch.empty((1, c, h + 2, w), dtype=torch.float32, device=dev, memory_format=_CL).zero_())
-        self.generation = 0
 
     def build(self, level_img: torch.Tensor):
         return ShardPathFn.apply(self, level_img)
@@ -169,7 +181,7 @@ class ShardedPyramid:
 
     def __init__(self, levels: List[ShardedPathLevel]):
         self.levels = list(levels)
-        self.lanes = Lanes(levels[0].xin.device, len(levels)) if MULTI_STREAM else _SERIAL
+        self.lanes = Lanes(levels[0].device, len(levels)) if MULTI_STREAM else _SERIAL
 
     def evaluate(self, optimizing_img: torch.Tensor):
         """image leaf -> summed loss over the levels (neural_style_transfer.py:168-185), differentiable."""
@@ -220,18 +232,21 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
         if tuple(im.shape) != (1, plan.steps[0][3], sh.H, sh.W):
             raise ValueError(f'sharded level expects {(1, plan.steps[0][3], sh.H, sh.W)}; got {tuple(im.shape)}')
         sh.generation += 1
+        if not sh.hb:
+            continue
         # image band + one row above / below straight from the replicated image (rows outside the image stay 0)
-        lo, hi = max(sh.band.r0 - 1, 0), min(sh.band.r1 + 1, sh.H)
+        lo, hi = max(sh.r0 - 1, 0), min(sh.r1 + 1, sh.H)
         c0 = im.shape[1]
         ops.chw_to_hwc(im, sh.xin, c0, (hi - lo) * sh.W, plane=sh.H * sh.W, x_off=lo * sh.W,
-                       y_off=(lo - (sh.band.r0 - 1)) * sh.W * c0)
+                       y_off=(lo - (sh.r0 - 1)) * sh.W * c0)
+    active = [li for li, sh in enumerate(levels) if sh.hb]       # the levels this rank owns rows of
     xs = [sh.xin for sh in levels]
     taps = [[None] * len(plan.tap_step) for _ in levels]
     for sidx in range(plan.n_steps_needed):
         st = plan.steps[sidx]
         if st[0] == 'conv' and sidx > 0:
-            with ops.timed(dev, ('halo_exchange_fwd', len(levels), sidx)):
-                par.halo_exchange(grp, [_rows(x) for x in xs])
+            with ops.timed(dev, ('halo_exchange_fwd', len(active), sidx)):
+                par.halo_exchange(grp, [(_rows(xs[li]), levels[li].up, levels[li].dn) for li in active])
         def step(li, st=st, sidx=sidx):
             x, y = xs[li], levels[li].bufs[sidx]
             if st[0] == 'conv':
@@ -244,7 +259,7 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
                 taps[li][k] = _interior(y)
             xs[li] = y
 
-        lanes.each(range(len(levels)), step)
+        lanes.each(active, step)
     # raw partial Grams + partial content SSE of every level -> ONE all-reduce -> identical finalize on every rank
     n_packed = sum((sh.n_packed + 3) // 4 * 4 for sh in levels)      # every level's block stays 16-byte aligned
     packed_all = torch.zeros(n_packed, dtype=torch.float32, device=dev)
@@ -263,7 +278,7 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
         ops.mse_fwd(taps[li][sh.cidx], sh.target_content_band, 1.0, packed[sh.content_slot],
                     sh.wss.for_reduce('content', dev))
 
-    lanes.each(range(len(levels)), partials)
+    lanes.each(active, partials)
     with ops.timed(dev, ('allreduce_packed_grams', n_packed)):
         grp.all_reduce_sum(packed_all)
     out4s, per_level = [], []
@@ -343,13 +358,15 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tenso
             d = torch.zeros_like(im)
         d_imgs.append(d)
     gps = [None] * len(levels)                  # padded gradient band w.r.t. the current step's output, per level
+    flowing = False                             # a tap at or below this step has started the gradient
     masked = [False] * len(levels)
     for sidx in range(plan.n_steps_needed - 1, -1, -1):
         st = plan.steps[sidx]
         has_tap = bool(plan.taps_at.get(sidx))
-        live = [li for li in range(len(levels)) if gps[li] is not None or has_tap]
-        if not live:
+        if not (has_tap or flowing):             # the same decision on every rank, whatever rows it owns
             continue
+        flowing = True
+        live = [li for li in range(len(levels)) if levels[li].hb]
         if st[0] == 'conv':
             def pre(li, sidx=sidx):              # tap gradients into the band + the ReLU's backward (fused or in place)
                 taps_here = plan.taps_at.get(sidx, ())
@@ -363,7 +380,8 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tenso
 
             lanes.each(live, pre)
             with ops.timed(dev, ('halo_exchange_bwd', len(live), sidx)):
-                par.halo_exchange(grp, [_rows(gps[li]) for li in live], zero_border=True)
+                par.halo_exchange(grp, [(_rows(gps[li]), levels[li].up, levels[li].dn) for li in live],
+                                  zero_border=True)
 
             def dgrad(li, st=st, sidx=sidx):
                 sh = levels[li]
@@ -374,7 +392,7 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tenso
                 else:
                     c0 = gxp.shape[1]
                     ops.hwc_to_chw(gxp, d_imgs[li], c0, sh.hb * sh.W, True, plane=sh.H * sh.W, x_off=sh.W * c0,
-                                   y_off=sh.band.r0 * sh.W)
+                                   y_off=sh.r0 * sh.W)
                     gps[li] = None
 
             lanes.each(live, dgrad)

@@ -225,6 +225,15 @@ def kernel_table(summary, pk):
     return rows
 
 
+_T0 = time.perf_counter()
+
+
+def phase(msg):
+    """Progress line on stderr (rank 0): where a bench run's wall time goes."""
+    if int(os.environ.get('RANK', '0')) == 0:
+        print(f'[bench +{time.perf_counter() - _T0:7.1f}s] {msg}', file=sys.stderr, flush=True)
+
+
 def build_job(args, dev):
     """Images, init and the _Job (leaf image + optimizer + per-level LossBuilders), as process() builds them."""
     import numpy as np
@@ -266,8 +275,10 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
         parallel.init_sharding()
     seeded_vgg_patch()
+    phase('library loaded')
     content_levels, style_levels, init, name, init_s = build_job(args, dev)
     H, W = init.shape[0], init.shape[1]
+    phase('images + init built')
     job = nst._Job(dev, 'vgg19', style_levels, args.optimizer, content_levels, init, 10.0, *WEIGHTS, name)
 
     def barrier():
@@ -275,6 +286,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    phase('job set up (targets, band plan)')
     # ---- device-resident timing ------------------------------------------------------------------------
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -282,6 +294,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         job.optimizer_step()          # the first closures run eagerly, then the closure is captured as a CUDA graph
     barrier()
+    phase('warm-up done (eager closures, cuDNN engine search, graph capture)')
     closures0 = job.step
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -293,6 +306,7 @@ def run_ours(args):
     barrier()
     clocks.window(w0, time.perf_counter())
     ms = e0.elapsed_time(e1)
+    phase('timed steps done')
     closures = job.step - closures0
     graphed = job._graph is not None
     if args.profile:
@@ -317,6 +331,7 @@ def run_ours(args):
         job.optimizer_step()
     barrier()
     probe_closures = job.step - c0
+    phase('per-kernel eager pass done')
     launches = int(round(ops.STATS.launches / max(probe_closures, 1) * closures))
     summary = ops.STATS.summary()
     for v in summary.values():
@@ -357,6 +372,7 @@ def run_ours(args):
             return t_start, time.perf_counter(), last
 
         (t0, step0), t1, (img, step1) = asyncio.run(drive())
+        phase('end-to-end pass through process() done')
         wall = t1 - t0
         if world > 1:
             t = torch.tensor([wall], device=dev)
@@ -416,6 +432,7 @@ def run_ours(args):
                                f'{args.optimizer}, structured-noise init (BASELINE configs[3])',
                    'levels': args.levels, 'image': [H, W], 'optimizer': args.optimizer,
                    'parallelism': f'rowband{world}' if world > 1 else 'single',
+                   'bands': parallel.PLAN.describe() if parallel.PLAN is not None else None,
                    'cache': f'working set {mem_gb:.1f} GB per step >> {L2_BYTES / 1e6:.0f} MB L2 (no flush needed)',
                    'closures_timed': closures, 'cuda_graph': graphed, 'cudnn_autotune': not args.no_cudnn_autotune, 'gram_operands': args.precision or ops.DEFAULT_PRECISION,
                    'vgg_convs': 'cuDNN via torch ops on channels_last tensors (out of scope)',
@@ -427,6 +444,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(steps=2, warmup=1, levels=args.levels)
+        phase('cpu baseline done')
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

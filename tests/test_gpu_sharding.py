@@ -17,6 +17,14 @@ def dev():
     return torch.device('cuda', 0)
 
 
+def root_causes(errors):
+    """The emulated ranks' failures with the aborted-barrier followers last (they only echo the first failure)."""
+    errors = sorted((str(e) for e in errors), key=lambda e: 'BrokenBarrierError' in e)
+    for e in errors[:2]:
+        print(e)                     # pytest's assertion repr truncates long strings; the captured stdout does not
+    return errors[:2]
+
+
 class ThreadGroup:
     """all_reduce_sum across `world` threads of this process (fixed rank order -> deterministic)."""
 
@@ -97,7 +105,7 @@ def test_sharded_level_matches_unsharded(seeded_vgg, world, precision):
         threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
         [t.start() for t in threads]
         [t.join() for t in threads]
-        assert not errors, errors
+        assert not errors, root_causes(errors)
     finally:
         nst.PRECISION = None
     tol = 2e-5 if precision == 'fp32' else 2e-4
@@ -159,7 +167,7 @@ def test_halo_exchange_level_matches_unsharded(seeded_vgg, world, H, W):
     threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
     [t.start() for t in threads]
     [t.join() for t in threads]
-    assert not errors, errors
+    assert not errors, root_causes(errors)
     for r in range(world):
         np.testing.assert_allclose(results[r][0], ref, rtol=1e-4)
         assert results[r][0] == results[0][0]                 # every rank sees bit-identical losses
@@ -175,30 +183,40 @@ def test_halo_exchange_level_matches_unsharded(seeded_vgg, world, H, W):
         assert float(gr[:, :, hi:].abs().max() if hi < H else 0.0) == 0.0
 
 
-@pytest.mark.timeout(240)
-@pytest.mark.parametrize('world', [2, 4])
-def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, world):
-    """Two pyramid levels evaluated in lock-step with grouped halo exchanges == the unsharded closure
-    (bicubic chain + both levels + backward), summed over the emulated ranks."""
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('world,bands,n_levels', [(2, 'uniform', 2), (4, 'uniform', 2), (2, 'pyramid', 3),
+                                                  (3, 'pyramid', 3), (4, 'pyramid', 3), (8, 'pyramid', 3)])
+def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, world, bands, n_levels):
+    """The pyramid levels evaluated in lock-step with grouped halo exchanges == the unsharded closure (bicubic chain
+    + every level + backward), summed over the emulated ranks.  'uniform': every level cut into `world` equal bands;
+    'pyramid': the level-aware plan (parallel.PyramidBands) — unequal bands, ranks that own rows of two levels, ranks
+    that own nothing of a level and are skipped by their neighbours' exchange."""
     from artstyletransfer_b200 import math_utils, neural_style_transfer as nst, ops
+    from artstyletransfer_b200.parallel import PyramidBands
     from artstyletransfer_b200.sharded_path import PyramidFn, ShardedPathLevel, ShardedPyramid
-    H, W = 256, 96
+    H, W = (256, 96) if n_levels == 2 else (256, 128)
     content, style = O.synthetic_images(H, W, seed=11)
     init = np.clip(content * 0.5 + np.random.default_rng(12).uniform(0, 1, size=content.shape) * 0.5, 0, 1).astype(np.float32)
     net, cidx, sidx = math_utils.prepare_model('vgg19', dev())
-    c_lv = [content, content[::2, ::2].copy()]
-    s_lv = [style, style[::2, ::2].copy()]
+    c_lv = [content[::1 << i, ::1 << i].copy() for i in range(n_levels)]
+    s_lv = [style[::1 << i, ::1 << i].copy() for i in range(n_levels)]
     c_img = [nst.prepare_img(c, dev()) for c in c_lv]
     s_img = [nst.prepare_img(s_, dev()) for s_ in s_lv]
     lbs = [nst.LossBuilder(cidx, sidx, c, s_, net, *WEIGHTS) for c, s_ in zip(c_img, s_img)]
     img = nst.prepare_img(init, dev()).requires_grad_(True)
-    lv1 = ops.bicubic_half(img)
-    t0 = lbs[0].build(img)[0]
-    t1 = lbs[1].build(lv1)[0]
-    total = 1.0 * t0 + t1
+    lv, total = img, None
+    for i in range(n_levels):
+        if i:
+            lv = ops.bicubic_half(lv)
+        t = lbs[i].build(lv)[0]
+        total = t if total is None else 1.0 * total + t
     total.backward()
     ref_total, ref_grad = total.item(), img.grad.clone()
     plan = lbs[0].path_plan(img)
+    sizes = [(H >> i, W >> i) for i in range(n_levels)]
+    pb = PyramidBands(sizes, world, uniform=bands == 'uniform')
+    if bands == 'pyramid' and world > 2:           # the plan really is heterogeneous at these sizes
+        assert any(pb.band(li, r)[0] == pb.band(li, r)[1] for li in range(n_levels) for r in range(world))
 
     shared = {'bufs': [None] * world, 'barrier': threading.Barrier(world, timeout=60), 'mail': {}}
     results = [None] * world
@@ -211,14 +229,19 @@ def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, world):
         try:
             torch.cuda.set_device(dev())
             grp = ThreadGroup(rank, world, shared)
-            levels = [ShardedPathLevel(grp, plan, c_img[i], s_img[i], cidx, sidx, WEIGHTS, H >> i, W >> i) for i in range(2)]
+            levels = [ShardedPathLevel(grp, plan, c_img[i], s_img[i], cidx, sidx, WEIGHTS, *sizes[i],
+                                       band=(*pb.band(i, rank), *pb.neighbours(i, rank))) for i in range(n_levels)]
             pyr = ShardedPyramid(levels)
-            x = nst.prepare_img(init, dev())
-            ctx = Ctx()
-            with torch.no_grad():
-                t = PyramidFn.forward(ctx, pyr, x)
-                _, g = PyramidFn.backward(ctx, None)
-            results[rank] = (t.item(), g.clone())
+            out = []
+            for _ in range(2):                      # persistent buffers: a second closure must agree bit for bit
+                x = nst.prepare_img(init, dev())
+                ctx = Ctx()
+                with torch.no_grad():
+                    t = PyramidFn.forward(ctx, pyr, x)
+                    _, g = PyramidFn.backward(ctx, None)
+                out.append((t.item(), g.clone()))
+            assert out[0][0] == out[1][0] and torch.equal(out[0][1], out[1][1])
+            results[rank] = out[0]
         except Exception:   # pragma: no cover
             import traceback
             errors.append(traceback.format_exc())
@@ -227,7 +250,7 @@ def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, world):
     threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
     [t.start() for t in threads]
     [t.join() for t in threads]
-    assert not errors, errors
+    assert not errors, root_causes(errors)
     for r in range(world):
         assert abs(results[r][0] - ref_total) <= 1e-4 * abs(ref_total)
         assert results[r][0] == results[0][0]

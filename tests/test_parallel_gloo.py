@@ -80,7 +80,7 @@ def test_band_sums_equal_full_grams_over_gloo():
     assert out[0][0] == out[1][0]              # all ranks hold identical reduced values
 
 
-def _halo_worker(rank, world, port, out):
+def _halo_worker(rank, world, port, out, edges=None):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
@@ -90,7 +90,22 @@ def _halo_worker(rank, world, port, out):
         parallel.init_sharding()
         grp = parallel._GROUP
         H, W, C1, C2 = 24, 10, 4, 6
-        hb = H // world
+        if edges is None:                          # equal bands, neighbours rank -+ 1 (halo_exchange's default)
+            edges = [r * (H // world) for r in range(world + 1)]
+            nb = None
+        else:                                      # explicit row edges; a rank may own nothing (parallel.PyramidBands)
+            owners = [r for r in range(world) if edges[r + 1] > edges[r]]
+            i = owners.index(rank) if rank in owners else None
+            nb = (None, None) if i is None else (owners[i - 1] if i > 0 else None,
+                                                 owners[i + 1] if i + 1 < len(owners) else None)
+        r0, r1 = edges[rank], edges[rank + 1]
+        hb = r1 - r0
+
+        def exchange(t, **kw):
+            if nb is None:
+                parallel.halo_exchange(grp, t, **kw)
+            else:
+                parallel.halo_exchange(grp, [(t, nb[0], nb[1])] if hb else [], **kw)
         g = torch.Generator().manual_seed(0)
         x = torch.randn((1, C1, H, W), generator=g, dtype=torch.float64)
         w1 = torch.randn((C2, C1, 3, 3), generator=g, dtype=torch.float64)
@@ -101,7 +116,6 @@ def _halo_worker(rank, world, port, out):
         yr = F.conv2d(F.conv2d(xr, w1, padding=1), w2, padding=1)
         (gref,) = torch.autograd.grad(yr, xr, gout)
         # sharded: each rank owns hb rows; padded NHWC bands, one halo row exchanged per convolution
-        r0, r1 = rank * hb, (rank + 1) * hb
 
         def padded(c):
             return torch.zeros((hb + 2, W, c), dtype=torch.float64)
@@ -110,12 +124,17 @@ def _halo_worker(rank, world, port, out):
             xin = pad_rows.permute(2, 0, 1)[None]
             return F.conv2d(xin, wgt, padding=(0, 1))[0].permute(1, 2, 0).contiguous()
 
+        if not hb:                                 # a rank without rows still walks through the four exchanges
+            for _ in range(4):
+                exchange(None)
+            out[rank] = (0.0, 0.0)
+            return
         a0 = padded(C1)
         a0[1:-1] = x[0, :, r0:r1].permute(1, 2, 0)
-        parallel.halo_exchange(grp, a0)
+        exchange(a0)
         a1 = padded(C2)
         a1[1:-1] = conv_band(a0, w1)
-        parallel.halo_exchange(grp, a1)
+        exchange(a1)
         y = conv_band(a1, w2)
         fwd_err = float((y - yr[0, :, r0:r1].permute(1, 2, 0)).abs().max())
 
@@ -129,9 +148,9 @@ def _halo_worker(rank, world, port, out):
 
         g1 = torch.full((hb + 2, W, C1), float('nan'), dtype=torch.float64)      # recycled buffer: halos are garbage
         g1[1:-1] = gout[0, :, r0:r1].permute(1, 2, 0)
-        parallel.halo_exchange(grp, g1, zero_border=True)
+        exchange(g1, zero_border=True)
         g0 = conv_band_bwd(g1, w2, C2)            # gradient w.r.t. the first convolution's output band (padded)
-        parallel.halo_exchange(grp, g0, zero_border=True)
+        exchange(g0, zero_border=True)
         gx = conv_band_bwd(g0, w1, C1)
         bwd_err = float((gx[1:-1] - gref[0, :, r0:r1].permute(1, 2, 0)).abs().max())
         out[rank] = (fwd_err, bwd_err)
@@ -151,6 +170,56 @@ def test_halo_exchange_reproduces_full_convolutions_over_gloo(world):
     for rank in range(world):
         fwd_err, bwd_err = out[rank]
         assert fwd_err < 1e-10 and bwd_err < 1e-10, (rank, fwd_err, bwd_err)
+
+
+@pytest.mark.parametrize('edges', [[0, 16, 24], [0, 8, 8, 24], [0, 0, 10, 24]])
+def test_halo_exchange_with_unequal_and_empty_bands_over_gloo(edges):
+    """The level-aware plan (parallel.PyramidBands): bands of different heights, and ranks that own no rows of a
+    level — their neighbours exchange across them, they join every step with an empty list."""
+    world = len(edges) - 1
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_halo_worker, args=(world, _free_port(), out, edges), nprocs=world, join=True)
+    assert sorted(out.keys()) == list(range(world))
+    for rank in range(world):
+        fwd_err, bwd_err = out[rank]
+        assert fwd_err < 1e-10 and bwd_err < 1e-10, (rank, fwd_err, bwd_err)
+
+
+def test_pyramid_bands_plan():
+    """Host logic of the level-aware band plan: every row of every level owned exactly once, 16-row edges, no band
+    under 32 rows, neighbours skip ranks without rows, and the modelled load balance at BASELINE's L=3 sizes."""
+    from artstyletransfer_b200.parallel import ALIGN, MIN_BAND_ROWS, PyramidBands
+    sizes = [(2048 >> i, 3072 >> i) for i in range(4)]
+    for world in (1, 2, 3, 4, 5, 8):
+        p = PyramidBands(sizes, world)
+        for li, (h, _) in enumerate(sizes):
+            edges = p.bounds[li]
+            assert len(edges) == world + 1 and edges[0] == 0 and edges[-1] == h
+            owners = []
+            for r in range(world):
+                r0, r1 = p.band(li, r)
+                assert r0 <= r1 and r0 % ALIGN == 0 and r1 % ALIGN == 0
+                assert r1 == r0 or r1 - r0 >= MIN_BAND_ROWS
+                if r1 > r0:
+                    owners.append(r)
+            for i, r in enumerate(owners):
+                assert p.neighbours(li, r) == (owners[i - 1] if i else None, owners[i + 1] if i + 1 < len(owners) else None)
+            for r in set(range(world)) - set(owners):
+                assert p.neighbours(li, r) == (None, None)
+        one = sum(PyramidBands(sizes, 1).loads())
+        assert one / max(p.loads()) > 0.85 * world, (world, p.describe())       # modelled strong-scaling efficiency
+        assert PyramidBands(sizes, world).bounds == p.bounds                   # deterministic: every rank plans alike
+    p8 = PyramidBands(sizes, 8)
+    assert sum(1 for r in range(8) if p8.band(0, r)[1] > p8.band(0, r)[0]) == 6   # the 2048x3072 level on six ranks
+    assert p8.band(3, 7) == (0, 256)                                           # the 256x384 level whole on the last
+    u = PyramidBands(sizes, 8, uniform=True)
+    assert [u.band(li, 3) for li in range(4)] == [(768, 1024), (384, 512), (192, 256), (96, 128)]
+    assert PyramidBands([(256, 64)], 8).bounds == [[32 * r for r in range(9)]]
+    with pytest.raises(ValueError):
+        PyramidBands([(250, 64)], 2)
+    with pytest.raises(ValueError):
+        PyramidBands([(96, 64)], 4, uniform=True)
 
 
 def test_init_sharding_requires_a_group():
