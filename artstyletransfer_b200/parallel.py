@@ -57,7 +57,7 @@ class BandPlan:
         return self.r0 // stride, self.r1 // stride
 
 
-BAND_OVERHEAD = float(os.environ.get('AST_BAND_OVERHEAD', '0.03'))
+BAND_OVERHEAD = float(os.environ.get('AST_BAND_OVERHEAD', '0.015'))
 MIN_BAND_ROWS = 2 * ALIGN
 
 

@@ -26,6 +26,13 @@ from . import parallel as par
 
 _CL = torch.channels_last
 MULTI_STREAM = os.environ.get('AST_LEVEL_STREAMS', '1') != '0'
+# '1': the band convolutions run as cuDNN's fused conv + bias + ReLU over the WHOLE padded band with symmetric
+# padding — (h + 2) rows in, (h + 2) rows out; the h owned rows only ever see real rows (their halos), the two outer
+# output rows saw the zero padding, are junk, and are exactly the halo rows of the next layer: the next exchange
+# overwrites them (at the image border they are zeroed).  Costs 2 / (h + 2) extra convolution rows and removes the
+# separate bias + ReLU pass (8 B per activation element, 3 ms of an unsharded L=3 closure).  '0': the convolution
+# writes the owned rows through cudnn_convolution.out into a persistent band, ast_bias_relu_nhwc follows.
+FUSED_BAND_CONV = os.environ.get('AST_SHARD_FUSED_CONV', '1') != '0'
 
 
 class Lanes:
@@ -119,7 +126,11 @@ class ShardedPathLevel:
                 c = st[4]
             else:
                 h, w = h // 2, w // 2
-            self.bufs.append(torch.empty((1, c, h + 2, w), dtype=torch.float32, device=dev, memory_format=_CL).zero_())
+            if st[0] == 'conv' and FUSED_BAND_CONV:
+                self.bufs.append(None)            # the fused convolution allocates its padded output every closure
+            else:
+                self.bufs.append(torch.empty((1, c, h + 2, w), dtype=torch.float32, device=dev,
+                                             memory_format=_CL).zero_())
 
     def build(self, level_img: torch.Tensor):
         return ShardPathFn.apply(self, level_img)
@@ -133,6 +144,14 @@ def _conv_fwd_into(x_pad, w, out):
     with ops.timed(x_pad.device, fp._ckey('cudnn_conv_fwd', out, w)):
         torch.ops.aten.cudnn_convolution.out(x_pad, w, [0, 1], [1, 1], [1, 1], 1, fp.CUDNN_BENCHMARK, False,
                                              torch.backends.cudnn.allow_tf32, out=out)
+
+
+def _conv_relu_fwd_padded(x_pad, w, b):
+    """cuDNN conv + bias + ReLU over the whole padded band (see FUSED_BAND_CONV): rows 1..h of the result are the
+    owned rows, rows 0 and h + 1 are to be overwritten."""
+    with ops.timed(x_pad.device, fp._ckey('cudnn_conv_bias_relu_fwd', x_pad, w)), fp._cudnn_mode():
+        y = torch.cudnn_convolution_relu(x_pad, w, b, [1, 1], [1, 1], [1, 1], 1)
+    return y if y.is_contiguous(memory_format=_CL) else y.contiguous(memory_format=_CL)
 
 
 def _conv_bwd_data_padded(g_pad, x_pad, w):
@@ -247,9 +266,20 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
         if st[0] == 'conv' and sidx > 0:
             with ops.timed(dev, ('halo_exchange_fwd', len(active), sidx)):
                 par.halo_exchange(grp, [(_rows(xs[li]), levels[li].up, levels[li].dn) for li in active])
-        def step(li, st=st, sidx=sidx):
-            x, y = xs[li], levels[li].bufs[sidx]
-            if st[0] == 'conv':
+        feeds_conv = sidx + 1 < plan.n_steps_needed and plan.steps[sidx + 1][0] == 'conv'
+
+        def step(li, st=st, sidx=sidx, feeds_conv=feeds_conv):
+            sh = levels[li]
+            x, y = xs[li], sh.bufs[sidx]
+            if st[0] == 'conv' and FUSED_BAND_CONV:
+                y = sh.bufs[sidx] = _conv_relu_fwd_padded(x, st[1], st[2])
+                if feeds_conv:                      # border halos are the next convolution's zero padding
+                    rows = _rows(y)
+                    if sh.up is None:
+                        rows[0].zero_()
+                    if sh.dn is None:
+                        rows[-1].zero_()
+            elif st[0] == 'conv':
                 yi = _interior(y)
                 _conv_fwd_into(x, st[1], yi)
                 ops.bias_relu_(yi, st[2])
