@@ -392,6 +392,8 @@ __global__ void __launch_bounds__(320, 1) gram_bwd_tc_kernel(const __grid_consta
                  bar_accf = smem_u32(bars + 3 * S), bar_acce = smem_u32(bars + 3 * S + 2),
                  bar_dfull = smem_u32(bars + 3 * S + 4), bar_dconv = smem_u32(bars + 3 * S + 5);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 6);
+  // q[epilogue warp][kOutBufs]: "the running-gradient block has landed in this output buffer" (fused ReLU backward)
+  const uint32_t bar_qall = smem_u32(bars + 3 * S + 7);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_tiles = ((int)blockIdx.x < P.n_tiles) ? (P.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -559,13 +561,16 @@ struct BwdNhwcParams {
   int C;
 };
 
-template <int C>
+// W ("wide epilogue", C = 256 only): 3 stages + 2 epilogue groups instead of 4 + 1 — the pipeline shape for the
+// fused ReLU backward, whose epilogue keeps one TMA load of the running gradient in flight per warp.
+template <int C, bool W = false>
 struct BwdNhwcCfg {
+  static_assert(!W || C == 256, "the wide-epilogue variant exists for C = 256 only");
   static constexpr bool kResidentD = (C <= 128);
   static constexpr int kFBytes = 128 * ROW_BYTES;                       // 16 KB: 128 positions x 32 channels
   static constexpr int kDChunkBytes = C * ROW_BYTES;                    // C rows x 32 k
   static constexpr int kStageBytes = kFBytes + (kResidentD ? 0 : kDChunkBytes);
-  static constexpr int kStages = (C == 512) ? 2 : ((C == 256 || C == 128) ? 4 : 6);
+  static constexpr int kStages = (C == 512) ? 2 : (C == 256 ? (W ? 3 : 4) : (C == 128 ? 4 : 6));
   static constexpr int kDResBytes = kResidentD ? C * C * 4 : 0;
   static constexpr int kAccBufs = (C == 512) ? 1 : 2;
   static constexpr int kTmemCols = (C == 64) ? 128 : (C == 128 ? 256 : 512);
@@ -574,20 +579,24 @@ struct BwdNhwcCfg {
   // epilogue groups of 4 warps (one warp per TMEM sub-partition); group e takes the 32-column groups g with
   // g % kEpiGroups == e.  Two groups where the epilogue also reads global memory (fused ReLU backward): the loads
   // in flight per SM, not the sectors per request, bound that path.
-  static constexpr int kEpiGroups = (C == 256) ? 1 : 2;   // measured: C = 256 is faster with 4 stages + 1 group
+  static constexpr int kEpiGroups = (C == 256 && !W) ? 1 : 2;   // measured: plain C = 256 is faster with 4 stages + 1 group
   static constexpr int kThreads = 192 + 128 * kEpiGroups;
-  static constexpr int kOutBytes = 4 * kEpiGroups * 2 * 4096;           // per epilogue warp: two 32 x 32 fp32 blocks
-  static constexpr int kSmemBytes = kStages * kStageBytes + kDResBytes + kOutBytes + 1024 + 256;
+  // per epilogue warp: kOutBufs 32 x 32 fp32 blocks.  Two are enough for store-only epilogues; the fused ReLU
+  // backward also LOADS the running gradient block through TMA into the buffer it will be stored from, and a third
+  // buffer keeps two loads in flight per warp (C = 64 / 128, where the shared-memory budget allows it).
+  static constexpr int kOutBufs = (C <= 128) ? 3 : 2;
+  static constexpr int kOutBytes = 4 * kEpiGroups * kOutBufs * 4096;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kDResBytes + kOutBytes + 1024 + 512;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 // warp 0: TMA loads, warp 1: MMA + TMEM, warps 2..5: converters, warps 6..: epilogue groups + TMA stores.
-template <int C>
-__global__ void __launch_bounds__(BwdNhwcCfg<C>::kThreads, 1) gram_bwd_nhwc_tc_kernel(const __grid_constant__ CUtensorMap tmapF,
+template <int C, bool W = false>
+__global__ void __launch_bounds__(BwdNhwcCfg<C, W>::kThreads, 1) gram_bwd_nhwc_tc_kernel(const __grid_constant__ CUtensorMap tmapF,
                                                                  const __grid_constant__ CUtensorMap tmapD,
                                                                  const __grid_constant__ CUtensorMap tmapO,
                                                                  const __grid_constant__ BwdNhwcParams P) {
-  using Cfg = BwdNhwcCfg<C>;
+  using Cfg = BwdNhwcCfg<C, W>;
   constexpr int S = Cfg::kStages;
   constexpr int KC = C / BK;            // K chunks per tile
   constexpr int NB = Cfg::kAccBufs;
@@ -601,6 +610,8 @@ __global__ void __launch_bounds__(BwdNhwcCfg<C>::kThreads, 1) gram_bwd_nhwc_tc_k
                  bar_accf = smem_u32(bars + 3 * S), bar_acce = smem_u32(bars + 3 * S + 2),
                  bar_dfull = smem_u32(bars + 3 * S + 4), bar_dconv = smem_u32(bars + 3 * S + 5);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 6);
+  // q[epilogue warp][kOutBufs]: "the running-gradient block has landed in this output buffer" (fused ReLU backward)
+  const uint32_t bar_qall = smem_u32(bars + 3 * S + 7);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_tiles = ((int)blockIdx.x < P.n_tiles) ? (P.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -619,6 +630,7 @@ __global__ void __launch_bounds__(BwdNhwcCfg<C>::kThreads, 1) gram_bwd_nhwc_tc_k
     }
     mbar_init(bar_dfull, 1);
     mbar_init(bar_dconv, 128);
+    for (int q = 0; q < 4 * Cfg::kEpiGroups * Cfg::kOutBufs; ++q) mbar_init(bar_qall + 8 * q, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -709,12 +721,100 @@ __global__ void __launch_bounds__(BwdNhwcCfg<C>::kThreads, 1) gram_bwd_nhwc_tc_k
       fence_proxy_async_smem();
       mbar_arrive(bar_conv + 8 * s);
     }
+  } else if (P.relu_mask && P.accumulate) {
+    // ===== epilogue with the fused ReLU backward on top of a running gradient =====
+    //   out = F > 0 ? s * acc + dF : 0.   The running-gradient block (32 positions x 32 channels, the HBM stream of
+    //   this path) arrives through TMA in the very buffer the result is stored from: lane 0 keeps kOutBufs - 1 block
+    //   loads in flight — independent of the accumulator, so they run ahead across tile boundaries — every lane
+    //   reads its 128-byte row with conflict-free LDS.128, writes the result back in place, and the buffer goes out
+    //   as a plain TMA store.  Only the mask still comes through per-thread loads (F is L2-hot: just staged).
+    constexpr int NBUF = Cfg::kOutBufs;
+    constexpr int GP = (C / 32) / Cfg::kEpiGroups;          // 32-channel blocks per tile for this epilogue group
+    const int ew = warp - 6;
+    const int sub = warp & 3;
+    const int egrp = ew >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(sub * 32) << 16);
+    const float scale = P.gscale ? P.scale * __ldg(P.gscale) : P.scale;
+    const uint32_t stg = smem_u32(ostage + ew * (NBUF * 4096));
+    const uint32_t bar_q = bar_qall + 8 * (ew * NBUF);
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    // tiles whose 32-position sub-block of this warp starts inside the tensor (a prefix of my_tiles)
+    int vt = 0;
+    while (vt < my_tiles && ((int64_t)blockIdx.x + (int64_t)vt * gridDim.x) * 128 + sub * 32 < P.HW) ++vt;
+    const int nblk = vt * GP;
+    auto issue = [&](int m) {                                // lane 0: running-gradient block m -> buffer m % NBUF
+      const int ti = m / GP, g = egrp + (m % GP) * Cfg::kEpiGroups;
+      const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * 128 + sub * 32;
+      const uint32_t bq = bar_q + 8 * (m % NBUF);
+      mbar_arrive_expect_tx(bq, 4096u);
+      tma_load_2d(stg + (uint32_t)(m % NBUF) * 4096u, &tmapO, bq, g * 32, (int)p0);
+    };
+    if (lane == 0)
+      for (int m = 0; m < NBUF - 1 && m < nblk; ++m) issue(m);
+    uint32_t v[32];
+    int m = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int b = ti % NB;
+      const uint32_t bph = (uint32_t)(ti / NB) & 1u;
+      const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * 128 + sub * 32;
+      mbar_wait(bar_accf + 8 * b, bph);
+      tc_fence_after();
+      if (ti < vt) {
+#pragma unroll 1
+        for (int gi = 0; gi < GP; ++gi, ++m) {
+          const int g = egrp + gi * Cfg::kEpiGroups;
+          const int64_t p = p0 + lane;
+          float4 f[8];
+          if (p < P.HW) {
+            const float4* fr = reinterpret_cast<const float4*>(P.F + p * C + g * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __ldg(fr + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (lane == 0) {
+            tma_store_wait_read<0>();                        // every earlier store has left its buffer
+            if (m + NBUF - 1 < nblk) issue(m + NBUF - 1);    // -> the buffer block m - 1 was stored from
+          }
+          tmem_ld_x32(lane_addr + b * C + g * 32, v);
+          tmem_ld_wait();
+          mbar_wait(bar_q + 8 * (m % NBUF), (uint32_t)(m / NBUF) & 1u);
+          const uint32_t buf = stg + (uint32_t)(m % NBUF) * 4096u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t addr = buf + row_off + ((((uint32_t)j) ^ sw) << 4);
+            float4 q;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                         : "r"(addr)
+                         : "memory");
+            q.x = f[j].x > 0.f ? __fadd_rn(__fmul_rn(scale, __uint_as_float(v[4 * j])), q.x) : 0.f;
+            q.y = f[j].y > 0.f ? __fadd_rn(__fmul_rn(scale, __uint_as_float(v[4 * j + 1])), q.y) : 0.f;
+            q.z = f[j].z > 0.f ? __fadd_rn(__fmul_rn(scale, __uint_as_float(v[4 * j + 2])), q.z) : 0.f;
+            q.w = f[j].w > 0.f ? __fadd_rn(__fmul_rn(scale, __uint_as_float(v[4 * j + 3])), q.w) : 0.f;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(q.x), "f"(q.y), "f"(q.z), "f"(q.w)
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmapO, buf, g * 32, (int)p0);
+            tma_store_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acce + 8 * b);
+    }
+    if (lane == 0) tma_store_wait<0>();
   } else {
     // ===== epilogue: TMEM -> registers -> swizzled shared block -> TMA store / reduce-add =====
     const int sub = warp & 3;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(sub * 32) << 16);
     const float scale = P.gscale ? P.scale * __ldg(P.gscale) : P.scale;
-    const uint32_t stg = smem_u32(ostage + (warp - 6) * 8192);
+    const uint32_t stg = smem_u32(ostage + (warp - 6) * (Cfg::kOutBufs * 4096));
     const int egrp = (warp - 6) >> 2;
     const uint32_t row_off = (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
@@ -1143,10 +1243,10 @@ int gram_tc_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, f
   return AST_ERR_UNSUPPORTED;
 }
 
-template <int C>
+template <int C, bool W = false>
 static int launch_bwd_nhwc(const float* D, const float* F, int64_t HW, float scale, const float* gscale, float* dF,
                            int accumulate, int d_prerounded, int relu_mask, int num_sms, cudaStream_t stream) {
-  using Cfg = BwdNhwcCfg<C>;
+  using Cfg = BwdNhwcCfg<C, W>;
   CUtensorMap tmF, tmD, tmO;
   int rc = make_tmap(&tmF, F, (uint64_t)HW, C, C, 128);
   if (rc != AST_OK) return rc;
@@ -1165,14 +1265,14 @@ static int launch_bwd_nhwc(const float* D, const float* F, int64_t HW, float sca
   P.F = F;
   P.dF = dF;
   P.C = C;
-  cudaError_t e = cudaFuncSetAttribute(gram_bwd_nhwc_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(gram_bwd_nhwc_tc_kernel<C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("gram_tc_bwd_nhwc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return AST_ERR_CUDA;
   }
   const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
-  gram_bwd_nhwc_tc_kernel<C><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmF, tmD, tmO, P);
+  gram_bwd_nhwc_tc_kernel<C, W><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmF, tmD, tmO, P);
   return check_launch("gram_bwd_nhwc_tc");
 }
 
@@ -1216,7 +1316,10 @@ int gram_tc_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float sc
   switch (C) {
     case 64: return launch_bwd_nhwc<64>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
     case 128: return launch_bwd_nhwc<128>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
-    case 256: return launch_bwd_nhwc<256>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
+    case 256:
+      if (relu_mask && accumulate)
+        return launch_bwd_nhwc<256, true>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
+      return launch_bwd_nhwc<256>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
     case 512: {
       // CTA-pair kernel by default; AST_GRAM_BWD_2CTA=0 selects the one-CTA kernel (comparison / fallback)
       static const int use_pair = (getenv("AST_GRAM_BWD_2CTA") && atoi(getenv("AST_GRAM_BWD_2CTA")) == 0) ? 0 : 1;

@@ -135,7 +135,8 @@ def test_prerounded_d_gives_bit_identical_backward(c, hw):
     assert rel(d2.cpu().numpy(), d0.cpu().numpy()) < 1e-3
 
 
-@pytest.mark.parametrize('c,hw', [(64, 100), (64, 4096 + 37), (128, 5000), (256, 3000), (512, 1536)])
+@pytest.mark.parametrize('c,hw', [(64, 100), (64, 40), (64, 4096 + 37), (64, 57000), (128, 5000), (128, 40001), (256, 3000),
+                                  (256, 39000), (512, 1536)])
 @pytest.mark.parametrize('accumulate', [False, True])
 def test_gram_bwd_nhwc_fused_relu_backward(c, hw, accumulate):
     """relu_mask: the kernel writes the gradient w.r.t. the ReLU's INPUT — bit-identical to the unfused sequence
