@@ -200,6 +200,8 @@ def ncu_traffic(kernel: str):
         return None
     if kernel.startswith('mse_bwd/') and kernel.count('/') == 2:
         kernel = kernel.rsplit('/', 1)[0]            # captured in accumulate mode
+    if kernel in table:
+        return table[kernel]
     if kernel.startswith('gram_bwd_nhwc/'):          # the fused-ReLU modes (2, 3) move the same DRAM bytes as 0, 1
         head, mode = kernel.rsplit('/', 1)
         kernel = f'{head}/{int(mode) & 1}'

@@ -1,7 +1,7 @@
 """Small target for `ncu --set full`: ONE launch of each hot kernel of the channels-last path at the L=3 top-level
 sizes (after one untimed warm-up launch each, which ncu skips with -s): the (HW, C) Gram forward / backward for the
 four VGG widths, the glue kernels on the largest activations, the content MSE, TV and the bicubic pyramid step.
-usage: python tests/tools/ncu_target.py [gram] [glue] [elementwise]   (default: all groups)"""
+usage: python tests/tools/ncu_target.py [gram] [relu] [glue] [elementwise]   (default: gram glue elementwise)"""
 import os
 import sys
 
@@ -32,6 +32,18 @@ for c, hw in ([(64, 6291456), (128, 1572864), (256, 393216), (512, 98304)] if 'g
     once(lambda: ops.gram_bwd_nhwc(d, f, c, hw, 1e-3, None, df, True))
     torch.cuda.synchronize()
     print(c, hw, float(loss))
+    del f, df
+
+# the fused ReLU backward on top of a running gradient (mode 3: what the closure launches at relu1_1 .. relu3_1)
+for c, hw in ([(64, 6291456), (128, 1572864), (256, 393216)] if 'relu' in GROUPS else []):
+    f = torch.relu(torch.randn((hw, c), device=dev)) * 0.25
+    d = torch.randn((c, c), device=dev) * 1e-3
+    d = ((d + d.t()) / 2).contiguous()
+    df = torch.randn((hw, c), device=dev) * 1e-3
+    ops.gram_bwd_nhwc(d, f, c, hw, 1e-3, None, df, True, relu_mask=True)      # warm-up (module load)
+    once(lambda: ops.gram_bwd_nhwc(d, f, c, hw, 1e-3, None, df, True, relu_mask=True))
+    torch.cuda.synchronize()
+    print('relu', c, hw)
     del f, df
 
 if 'glue' not in GROUPS and 'elementwise' not in GROUPS:
