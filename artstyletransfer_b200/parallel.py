@@ -156,6 +156,12 @@ class PyramidBands:
             key = (round(max(self.loads(bounds)), 9), n_bands)
             if best is None or key < best[0]:
                 best = (key, bounds)
+        if all(BandPlan.shardable(h, self.world) for h, _ in self.sizes):
+            # tiny pyramids, where the 16-row granularity dominates: equal bands of every level can still win
+            bounds = [[r * (h // self.world) for r in range(self.world + 1)] for h, _ in self.sizes]
+            key = (round(max(self.loads(bounds)), 9), len(self.sizes) * self.world)
+            if key < best[0]:
+                best = (key, bounds)
         return best[1]
 
     # -- queries --------------------------------------------------------------------------------------------

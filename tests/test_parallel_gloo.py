@@ -228,3 +228,29 @@ def test_init_sharding_requires_a_group():
     with pytest.raises(RuntimeError, match='process group'):
         parallel.init_sharding()
     assert parallel.world() == (0, 1)
+
+
+def test_pyramid_bands_random_pyramids():
+    """Property test of the level-aware plan over random pyramids and world sizes: complete, aligned, no slivers,
+    never worse (in the model) than cutting every level into equal bands when that is possible."""
+    from hypothesis import given, settings, strategies as st
+    from artstyletransfer_b200.parallel import ALIGN, MIN_BAND_ROWS, BandPlan, PyramidBands
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(2, 40), st.integers(1, 24), st.integers(1, 4), st.integers(1, 8),
+           st.sampled_from([0.0, 0.015, 0.05]))
+    def check(h16, w16, n_levels, world, overhead):
+        h0, w0 = h16 * ALIGN << (n_levels - 1), w16 * ALIGN << (n_levels - 1)
+        sizes = [(h0 >> i, w0 >> i) for i in range(n_levels)]
+        p = PyramidBands(sizes, world, overhead=overhead)
+        for li, (h, _) in enumerate(sizes):
+            edges = p.bounds[li]
+            assert edges[0] == 0 and edges[-1] == h and len(edges) == world + 1
+            for r in range(world):
+                rows = edges[r + 1] - edges[r]
+                assert rows >= 0 and edges[r] % ALIGN == 0 and (rows == 0 or rows >= MIN_BAND_ROWS)
+        if all(BandPlan.shardable(h, world) for h, _ in sizes):
+            u = PyramidBands(sizes, world, overhead=overhead, uniform=True)
+            assert max(p.loads()) <= max(u.loads()) + 1e-9, (sizes, world, p.describe())
+
+    check()
