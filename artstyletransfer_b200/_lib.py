@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libast_sm100.so')
 
-AST_ABI_VERSION = 2
+AST_ABI_VERSION = 3
 AST_PREC_TF32, AST_PREC_FP32 = 0, 1
 AST_LAYOUT_CHW, AST_LAYOUT_HWC = 0, 1
 AST_COORD_TORCH, AST_COORD_CV2 = 0, 1
@@ -29,6 +29,14 @@ class NoiseLevel(C.Structure):
                 ('central', C.c_double), ('peripheral', C.c_double)]
 
 
+class HaloRow(C.Structure):
+    """struct ast_halo_row (include/ast_sm100.h)."""
+    _fields_ = [('src', C.c_void_p), ('dst_remote', C.c_void_p), ('stage', C.c_void_p), ('halo', C.c_void_p),
+                ('flag_remote', C.c_void_p), ('flag_local', C.c_void_p), ('state', C.c_void_p),
+                ('bytes', C.c_int64), ('slot_stride', C.c_int64)]
+
+
+AST_HALO_MAX_ROWS = 16
 _p, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 
 # name -> (restype, argtypes); one entry per declaration in include/ast_sm100.h
@@ -60,6 +68,7 @@ SIGNATURES = {
     'ast_bicubic_resize': (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p]),
     'ast_bicubic_resize_adj': (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     'ast_noise_init': (_i, [_p, _i, _i, C.POINTER(NoiseLevel), _i, _d, _i, _i, _d, _d, _p, _p]),
+    'ast_halo_exchange': (_i, [C.POINTER(HaloRow), _i, _p]),
 }
 
 _lib = None

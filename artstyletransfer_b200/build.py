@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libast_sm100.so')
-SOURCES = ['capi.cu', 'elementwise.cu', 'bicubic.cu', 'noise_init.cu', 'gram.cu', 'gram_tc.cu', 'vgg_glue.cu']
+SOURCES = ['capi.cu', 'elementwise.cu', 'bicubic.cu', 'noise_init.cu', 'gram.cu', 'gram_tc.cu', 'vgg_glue.cu', 'halo.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

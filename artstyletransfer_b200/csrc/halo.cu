@@ -1,0 +1,120 @@
+// Halo-row exchange between row-band neighbours through NVLink peer memory (ast_halo_exchange).
+//
+// One launch replaces the grouped NCCL send/recv of one lock-step step (parallel.halo_exchange): every entry is a
+// symmetric exchange with ONE neighbour — push my edge row into the neighbour's staging slot with plain 16-byte
+// stores over NVLink, publish an arrival counter with a system-scope release store, spin on my own counter with
+// acquire loads until the neighbour's row has landed in MY staging slot, copy it into my halo row.  Entries with
+// src == NULL zero a halo row instead (gradient bands at the image border).
+//
+// Protocol per entry (all state is per (level, direction), so entries never interfere):
+//   count      local, exchanges completed so far; seq = count + 1 identifies this exchange on BOTH sides (neighbours
+//              run the same number of exchanges), so nothing per-launch has to be passed in and a CUDA-graph replay
+//              advances by itself;
+//   staging    two slots per entry, selected by seq & 1.  A slot is overwritten at exchange e + 2, which the writer
+//              reaches only after it has seen the reader's counter for e + 1, which the reader publishes in a later
+//              launch than the one that drained the slot at e (stream order): no write-after-read hazard;
+//   tickets    two self-resetting counters find the last CTA of a row: the one that publishes the arrival counter
+//              after every CTA's stores, and the one that advances `count` after every CTA has read it.
+// The CTAs of one launch must be co-resident (they spin on the neighbour, whose progress needs our stores):
+// grid = 8 x n_rows <= 128 CTAs of 512 threads, a fraction of the machine.  A spin that lasts ~4 s traps.
+#include "ast_common.cuh"
+
+namespace ast {
+
+struct HaloArgs {
+  ast_halo_row rows[AST_HALO_MAX_ROWS];
+};
+
+constexpr int kHaloCtas = 8;
+constexpr int kHaloThreads = 512;
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kHaloThreads) halo_exchange_kernel(const __grid_constant__ HaloArgs A) {
+  const ast_halo_row& r = A.rows[blockIdx.y];
+  const int64_t n16 = r.bytes >> 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint4* halo = reinterpret_cast<uint4*>(r.halo);
+  if (r.src == nullptr) {
+    for (int64_t i = i0; i < n16; i += stride) halo[i] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  __shared__ uint32_t s_seq;
+  if (threadIdx.x == 0) s_seq = reinterpret_cast<volatile uint32_t*>(r.state)[0] + 1u;
+  __syncthreads();
+  const uint32_t seq = s_seq;
+  const int64_t slot = (int64_t)(seq & 1u) * r.slot_stride;
+
+  // ---- push my edge row into the neighbour's staging slot (loads batched so four are in flight per thread)
+  const uint4* src = reinterpret_cast<const uint4*>(r.src);
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(r.dst_remote) + slot);
+  int64_t i = i0;
+  for (; i + 3 * stride < n16; i += 4 * stride) {
+    const uint4 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+    dst[i] = a;
+    dst[i + stride] = b;
+    dst[i + 2 * stride] = c;
+    dst[i + 3 * stride] = d;
+  }
+  for (; i < n16; i += stride) dst[i] = src[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();                                   // this CTA's stores before its ticket
+    const uint32_t t = atomicAdd(&r.state[1], 1u);
+    if (t == gridDim.x - 1) {                                 // every CTA of the row has stored
+      r.state[1] = 0u;
+      __threadfence_system();
+      st_release_sys(r.flag_remote, seq);
+    }
+    // ---- wait until the neighbour's row for this exchange has landed in my staging slot
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(r.flag_local) - seq) < 0) {
+      if (clock64() - t0 > 8000000000LL) __trap();            // ~4 s: the neighbour is gone
+    }
+  }
+  __syncthreads();
+  const uint4* stg = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(r.stage) + slot);
+  for (int64_t k = i0; k < n16; k += stride) halo[k] = __ldcg(stg + k);     // L2 only: the peer wrote it
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t t = atomicAdd(&r.state[2], 1u);
+    if (t == gridDim.x - 1) {                                 // every CTA has read `count`: advance it
+      r.state[2] = 0u;
+      __threadfence();
+      reinterpret_cast<volatile uint32_t*>(r.state)[0] = seq;
+    }
+  }
+}
+
+}  // namespace ast
+
+extern "C" int ast_halo_exchange(const ast_halo_row* rows, int n_rows, void* stream) {
+  using namespace ast;
+  AST_REQUIRE(rows != nullptr && n_rows > 0 && n_rows <= AST_HALO_MAX_ROWS, AST_ERR_INVALID,
+              "ast_halo_exchange: n_rows must be 1..%d (got %d)", AST_HALO_MAX_ROWS, n_rows);
+  HaloArgs args = {};
+  for (int k = 0; k < n_rows; ++k) {
+    const ast_halo_row& r = rows[k];
+    AST_REQUIRE(r.halo != nullptr && r.bytes > 0 && (r.bytes & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(r.halo) & 15) == 0,
+                AST_ERR_INVALID, "ast_halo_exchange: row %d: halo must be 16-byte aligned, bytes a multiple of 16", k);
+    if (r.src != nullptr) {
+      AST_REQUIRE(r.dst_remote && r.stage && r.flag_remote && r.flag_local && r.state && (r.slot_stride & 15) == 0 &&
+                      r.slot_stride >= r.bytes && (reinterpret_cast<uintptr_t>(r.src) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(r.dst_remote) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(r.stage) & 15) == 0,
+                  AST_ERR_INVALID, "ast_halo_exchange: row %d: null or misaligned exchange pointers", k);
+    }
+    args.rows[k] = r;
+  }
+  halo_exchange_kernel<<<dim3(kHaloCtas, n_rows), kHaloThreads, 0, static_cast<cudaStream_t>(stream)>>>(args);
+  return check_launch("halo_exchange");
+}

@@ -217,10 +217,98 @@ class TorchDistGroup:
             work.wait()
 
 
+class PeerHaloGroup(TorchDistGroup):
+    """EXPERIMENTAL (AST_HALO=peer; compiled and argument-checked, NOT yet run on hardware — round 2 validates it at
+    2 GPUs under a timeout before it may become the default).  The halo rows of one lock-step step travel through
+    NVLink peer memory in ONE launch of ast_halo_exchange (csrc/halo.cu) instead of a grouped NCCL send/recv
+    (~35 us per step, 25 steps per closure = 0.9 ms of a 5.4 ms step at 8 GPUs): every rank owns a symmetric
+    buffer (torch.distributed._symmetric_memory) with a pair of staging slots and an arrival counter per
+    (pyramid level, direction); a neighbour pushes its edge row into my slot, bumps my counter, and the same kernel
+    copies the staged row into my halo.  The all-reduces stay on NCCL."""
+
+    MAX_LEVELS = 8
+
+    def __init__(self):
+        super().__init__()
+        self._hdl = None
+
+    def prepare(self, device: torch.device, row_bytes: int) -> None:
+        """Collective: (re)allocate the symmetric buffer for rows of up to row_bytes and reset every counter."""
+        import torch.distributed._symmetric_memory as symm_mem
+        slot = (int(row_bytes) + 255) // 256 * 256
+        n_entries = 2 * self.MAX_LEVELS                       # (level, from-above / from-below)
+        flags_bytes = 256 * n_entries                         # one counter per 256-byte line
+        need = flags_bytes + n_entries * 2 * slot
+        if self._hdl is None or self._slot < slot:
+            enable = getattr(symm_mem, 'enable_symm_mem_for_group', None)
+            if enable is not None:
+                try:
+                    enable(dist.group.WORLD.group_name)
+                except Exception:
+                    pass
+            self._buf = symm_mem.empty(need, dtype=torch.uint8, device=device)
+            self._hdl = symm_mem.rendezvous(self._buf, dist.group.WORLD)
+            self._ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+            self._slot, self._flags_bytes = slot, flags_bytes
+            self._state = torch.zeros(n_entries * 64, dtype=torch.int32, device=device)   # 256 B per entry
+        torch.cuda.synchronize(device)
+        dist.barrier()                                        # nobody is still exchanging with the old counters
+        self._buf.zero_()
+        self._state.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier()
+
+    def _entry(self, level: int, direction: int) -> int:
+        if not 0 <= level < self.MAX_LEVELS:
+            raise ValueError(f'peer halo exchange supports {self.MAX_LEVELS} pyramid levels; got level {level}')
+        return 2 * level + direction
+
+    def exchange_rows(self, entries, zero_border: bool) -> None:
+        from . import _lib as L, ops
+        if self._hdl is None:
+            raise RuntimeError('PeerHaloGroup.prepare() has not run (parallel.maybe_shard calls it)')
+        rows = []
+
+        def add(src, halo, peer, mine, theirs):
+            """mine: my entry (the slot pair the neighbour fills); theirs: the neighbour's entry that I fill."""
+            nbytes = halo.numel() * 4
+            if nbytes > self._slot:
+                raise ValueError(f'halo row of {nbytes} bytes exceeds the staging slot ({self._slot})')
+            r = L.HaloRow()
+            r.halo, r.bytes, r.slot_stride = halo.data_ptr(), nbytes, self._slot
+            if src is not None:
+                r.src = src.data_ptr()
+                r.dst_remote = self._ptrs[peer] + self._flags_bytes + theirs * 2 * self._slot
+                r.flag_remote = self._ptrs[peer] + 256 * theirs
+                r.stage = self._ptrs[self.rank] + self._flags_bytes + mine * 2 * self._slot
+                r.flag_local = self._ptrs[self.rank] + 256 * mine
+                r.state = self._state.data_ptr() + 256 * mine
+            rows.append(r)
+
+        dev = None
+        for r, up, dn, level in entries:
+            dev = r.device
+            h = r.shape[0] - 2
+            # my "from above" entry (direction 0) pairs with the upper neighbour's "from below" entry (1)
+            if up is not None:
+                add(r[1], r[0], up, self._entry(level, 0), self._entry(level, 1))
+            elif zero_border:
+                add(None, r[0], None, 0, 0)
+            if dn is not None:
+                add(r[h], r[h + 1], dn, self._entry(level, 1), self._entry(level, 0))
+            elif zero_border:
+                add(None, r[h + 1], None, 0, 0)
+        for i in range(0, len(rows), L.AST_HALO_MAX_ROWS):
+            chunk = rows[i:i + L.AST_HALO_MAX_ROWS]
+            arr = (L.HaloRow * len(chunk))(*chunk)
+            ops._launch(dev, ('halo_exchange', len(chunk)), 'ast_halo_exchange', arr, len(chunk))
+
+
 def halo_exchange(group, rows, zero_border: bool = False) -> None:
     """rows: one (h + 2, w, C) contiguous view of a padded band, or a list of them (row 0 and row h+1 are the
-    halos); a list entry may also be (view, up, dn) naming the ranks that own the rows above / below this band
-    (None at the image border) — the default is rank - 1 / rank + 1, the plan of equal bands.  Sends the first /
+    halos); a list entry may also be (view, up, dn[, level]) naming the ranks that own the rows above / below this
+    band (None at the image border) — the default is rank - 1 / rank + 1, the plan of equal bands — and the index
+    of the pyramid level (only the peer-memory group needs it: one staging slot pair per level and direction).  Sends the first /
     last owned row of every band to its neighbours and receives their edge rows into the halos, all in ONE grouped
     exchange (called with an empty list by a rank that has no band at this step, so emulated collectives stay in
     step; over NCCL that is a no-op).
@@ -232,14 +320,18 @@ def halo_exchange(group, rows, zero_border: bool = False) -> None:
     row outside the image, so a border halo is zeroed (gradient buffers are recycled, unlike activation bands)."""
     if torch.is_tensor(rows):
         rows = [rows]
-    sends, recvs = [], []
-    for entry in rows:
+    entries = []
+    for n, entry in enumerate(rows):
         if torch.is_tensor(entry):
-            r = entry
-            up = group.rank - 1 if group.rank > 0 else None
-            dn = group.rank + 1 if group.rank + 1 < group.world else None
+            entries.append((entry, group.rank - 1 if group.rank > 0 else None,
+                            group.rank + 1 if group.rank + 1 < group.world else None, n))
         else:
-            r, up, dn = entry
+            entries.append(tuple(entry) if len(entry) == 4 else (*entry, n))
+    if hasattr(group, 'exchange_rows'):          # one peer-memory kernel for the whole step (PeerHaloGroup)
+        group.exchange_rows(entries, zero_border)
+        return
+    sends, recvs = [], []
+    for r, up, dn, _ in entries:
         h = r.shape[0] - 2
         if up is not None:
             sends.append((r[1], up))
@@ -270,7 +362,7 @@ def init_sharding(group=None) -> None:
     if group is None:
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError('init_sharding() needs an initialized torch.distributed process group')
-        group = TorchDistGroup()
+        group = PeerHaloGroup() if os.environ.get('AST_HALO', 'nccl') == 'peer' else TorchDistGroup()
     _GROUP = group
 
 
@@ -427,6 +519,8 @@ def maybe_shard(loss_builders, optimizing_img, neural_net, content_idx, style_id
         for i, (lh, lw) in enumerate(sizes))
     if whole and not (uniform and not all(BandPlan.shardable(lh, world_) for lh, _ in sizes)):
         PLAN = PyramidBands(sizes, world_, uniform=uniform)
+        if hasattr(_GROUP, 'prepare'):           # peer-memory halo exchange: symmetric staging for the widest row
+            _GROUP.prepare(optimizing_img.device, 4 * 64 * sizes[0][1])
         for i, lb in enumerate(loss_builders):
             r0, r1 = PLAN.band(i, rank)
             up, dn = PLAN.neighbours(i, rank)

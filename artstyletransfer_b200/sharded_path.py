@@ -265,7 +265,7 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
         st = plan.steps[sidx]
         if st[0] == 'conv' and sidx > 0:
             with ops.timed(dev, ('halo_exchange_fwd', len(active), sidx)):
-                par.halo_exchange(grp, [(_rows(xs[li]), levels[li].up, levels[li].dn) for li in active])
+                par.halo_exchange(grp, [(_rows(xs[li]), levels[li].up, levels[li].dn, li) for li in active])
         feeds_conv = sidx + 1 < plan.n_steps_needed and plan.steps[sidx + 1][0] == 'conv'
 
         def step(li, st=st, sidx=sidx, feeds_conv=feeds_conv):
@@ -410,7 +410,7 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tenso
 
             lanes.each(live, pre)
             with ops.timed(dev, ('halo_exchange_bwd', len(live), sidx)):
-                par.halo_exchange(grp, [(_rows(gps[li]), levels[li].up, levels[li].dn) for li in live],
+                par.halo_exchange(grp, [(_rows(gps[li]), levels[li].up, levels[li].dn, li) for li in live],
                                   zero_border=True)
 
             def dgrad(li, st=st, sidx=sidx):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 2
+#define AST_ABI_VERSION 3
 
 #define AST_OK               0
 #define AST_ERR_INVALID     -1   /* bad argument (null pointer, non-positive size, misalignment) */
@@ -130,6 +130,32 @@ int ast_maxpool2x2_bwd_nhwc(const float* gy, const float* x, int C, int H, int W
 int ast_chw_to_hwc(const float* x, int C, int64_t HW, int64_t plane_stride, float* y, void* stream);
 int ast_hwc_to_chw(const float* x, int C, int64_t HW, float* y, int64_t plane_stride, int accumulate,
                    void* stream);
+
+/* ---- Halo rows of a row-band sharded level through NVLink peer memory (EXPERIMENTAL, off by default) ------
+ * The reference has no multi-GPU path (a commented-out device round-robin, neural_style_transfer.py:238-243);
+ * this replaces the grouped NCCL send/recv that parallel.halo_exchange issues before every 3x3 convolution of a
+ * band (and for the gradient rows in the backward) by ONE launch: every entry pushes `src` (my edge row) into the
+ * neighbour's staging slot with stores over NVLink, publishes an arrival counter (release, system scope), waits for
+ * the neighbour's row to land in MY staging slot and copies it into `halo`.  src == NULL: zero `halo` (border).
+ *   dst_remote / flag_remote : the NEIGHBOUR's staging slot pair and arrival counter, peer-mapped into this process
+ *                              (torch symmetric memory: _SymmetricMemory.buffer_ptrs);
+ *   stage / flag_local       : my staging slot pair and arrival counter (the neighbour writes them);
+ *   slot_stride              : bytes between the two slots of a pair (double buffering by exchange parity);
+ *   state                    : 3 zero-initialised uint32 in LOCAL memory {exchanges done, ticket, ticket};
+ *   both sides must run the same sequence of exchanges; counters are never reset by the kernel. */
+#define AST_HALO_MAX_ROWS 16
+typedef struct ast_halo_row {
+  const void* src;
+  void*       dst_remote;
+  const void* stage;
+  void*       halo;
+  uint32_t*   flag_remote;
+  uint32_t*   flag_local;
+  uint32_t*   state;
+  int64_t     bytes;
+  int64_t     slot_stride;
+} ast_halo_row;
+int ast_halo_exchange(const ast_halo_row* rows, int n_rows, void* stream);
 
 /* ---- Total variation (math_utils.py:37-41) -------------------------------------------------
  *   sums[0] = sum |y[..., :-1] - y[..., 1:]|,  sums[1] = sum |y[:, :-1, :] - y[:, 1:, :]|

@@ -34,7 +34,7 @@ def test_header_symbols_are_exported_and_bound(lib):
 
 
 def test_version_and_sizes(lib):
-    assert lib.ast_version() == 2
+    assert lib.ast_version() == 3
     assert lib.ast_reduce_workspace_bytes() >= 16384
     # workspace covers 148 split-K partials of the largest tile plus the reduce header
     assert lib.ast_gram_workspace_bytes(512, 98304) == 32768 + 148 * 256 * 256 * 4
@@ -54,6 +54,11 @@ def test_argument_validation_without_gpu(lib):
     assert rc == -3 and b'multiple of 64' in lib.ast_last_error()
     rc = lib.ast_gram_mse_fwd(p, 64, 64, 64, 1.0, None, p, None, p, 16, 0, None)
     assert rc == -4
+    rows = (_lib.HaloRow * 1)()
+    assert lib.ast_halo_exchange(rows, 0, None) == -1 and lib.ast_halo_exchange(rows, 17, None) == -1
+    assert lib.ast_halo_exchange(rows, 1, None) == -1 and b'halo must be' in lib.ast_last_error()
+    rows[0].halo, rows[0].bytes, rows[0].src = p + (-p % 16), 32, p + (-p % 16)
+    assert lib.ast_halo_exchange(rows, 1, None) == -1 and b'exchange pointers' in lib.ast_last_error()
     with pytest.raises(RuntimeError, match='ast_mse_bwd failed'):
         _lib.call('ast_mse_bwd', None, None, 1, 1.0, None, None, 0, 0, None)
 
