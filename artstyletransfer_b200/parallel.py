@@ -218,8 +218,8 @@ class TorchDistGroup:
 
 
 class PeerHaloGroup(TorchDistGroup):
-    """EXPERIMENTAL (AST_HALO=peer; compiled and argument-checked, NOT yet run on hardware — round 2 validates it at
-    2 GPUs under a timeout before it may become the default).  The halo rows of one lock-step step travel through
+    """EXPERIMENTAL (AST_HALO=peer; the kernel passes its one-GPU loop-back test, this class has NOT yet run between
+    two processes — round 2 validates it at 2 GPUs under a timeout before it may become the default).  The halo rows of one lock-step step travel through
     NVLink peer memory in ONE launch of ast_halo_exchange (csrc/halo.cu) instead of a grouped NCCL send/recv
     (~35 us per step, 25 steps per closure = 0.9 ms of a 5.4 ms step at 8 GPUs): every rank owns a symmetric
     buffer (torch.distributed._symmetric_memory) with a pair of staging slots and an arrival counter per

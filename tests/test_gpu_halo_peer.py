@@ -1,16 +1,11 @@
-"""GPU, EXPERIMENTAL (skipped unless AST_TEST_EXPERIMENTAL=1): ast_halo_exchange in loop-back on ONE device — two
-emulated neighbours A and B whose entries travel in the same launch, each one's "remote" pointers aimed at the
-other's staging slots and counters.  Exercises the whole protocol (push, release/acquire counters, slot parity,
-self-resetting tickets, count advance) over several consecutive exchanges; the real two-process run over NVLink is
-bench.py with AST_HALO=peer under torchrun."""
-import os
-
+"""GPU: ast_halo_exchange in loop-back on ONE device — two emulated neighbours A and B whose entries travel in the
+same launch, each one's "remote" pointers aimed at the other's staging slots and counters.  Exercises the whole protocol (push, release/acquire counters, slot parity,
+self-resetting tickets, count advance) over several consecutive exchanges (passed on a B200 in round 1); the
+two-process run over NVLink is bench.py with AST_HALO=peer under torchrun (pending: round 2)."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('AST_TEST_EXPERIMENTAL') != '1',
-                                 reason='peer-memory halo exchange is not validated on hardware yet (round 2)')]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.timeout(60)
