@@ -298,10 +298,13 @@ class PeerHaloGroup(TorchDistGroup):
                 add(r[h], r[h + 1], dn, self._entry(level, 1), self._entry(level, 0))
             elif zero_border:
                 add(None, r[h + 1], None, 0, 0)
-        for i in range(0, len(rows), L.AST_HALO_MAX_ROWS):
-            chunk = rows[i:i + L.AST_HALO_MAX_ROWS]
-            arr = (L.HaloRow * len(chunk))(*chunk)
-            ops._launch(dev, ('halo_exchange', len(chunk)), 'ast_halo_exchange', arr, len(chunk))
+        if not rows:
+            return
+        if len(rows) > L.AST_HALO_MAX_ROWS:
+            # never split a step over two launches: neighbours could then wait on each other's second launch
+            raise ValueError(f'{len(rows)} halo rows in one step; ast_halo_exchange takes {L.AST_HALO_MAX_ROWS}')
+        arr = (L.HaloRow * len(rows))(*rows)
+        ops._launch(dev, ('halo_exchange', len(rows)), 'ast_halo_exchange', arr, len(rows))
 
 
 def halo_exchange(group, rows, zero_border: bool = False) -> None:

@@ -254,3 +254,62 @@ def test_pyramid_bands_random_pyramids():
             assert max(p.loads()) <= max(u.loads()) + 1e-9, (sizes, world, p.describe())
 
     check()
+
+
+def test_peer_halo_group_pairs_slots_and_counters(monkeypatch):
+    """Host logic of parallel.PeerHaloGroup.exchange_rows (no GPU, no symmetric memory: fake peer pointers): what rank
+    A pushes for its lower neighbour B lands in exactly the slot pair / counter B waits on, and vice versa, per
+    level; border halos become zero-fill rows; one step is one launch (more than 16 rows are refused)."""
+    from artstyletransfer_b200 import _lib as L, ops, parallel
+    launched = {}
+
+    def fake_launch(dev, key, name, arr, n):
+        assert name == 'ast_halo_exchange' and 1 <= n <= L.AST_HALO_MAX_ROWS
+        launched.setdefault('rows', []).extend(
+            {f: getattr(arr[i], f) for f, _ in L.HaloRow._fields_} for i in range(n))
+        launched['calls'] = launched.get('calls', 0) + 1
+
+    monkeypatch.setattr(ops, '_launch', fake_launch)
+    base = {0: 0x10000000, 1: 0x20000000, 2: 0x30000000}
+    slot, flags_bytes = 4096, 256 * 16
+
+    def group(rank):
+        g = object.__new__(parallel.PeerHaloGroup)
+        g.rank, g.world, g._hdl = rank, 3, object()
+        g._ptrs, g._slot, g._flags_bytes = [base[0], base[1], base[2]], slot, flags_bytes
+        g._state = torch.zeros(16 * 64, dtype=torch.int32)
+        return g
+
+    def rows_of(rank, entries, zero_border):
+        launched.clear()
+        parallel.halo_exchange(group(rank), entries, zero_border=zero_border)
+        return launched['rows'], launched['calls']
+
+    band = {r: [torch.zeros(6, 8, 4) for _ in range(2)] for r in range(3)}       # two levels per rank
+    # level 0 lives on ranks 0, 1; level 1 on ranks 1, 2 (rank 1 owns rows of both: up = 0 at level 0, dn = 2 at level 1)
+    a, _ = rows_of(0, [(band[0][0], None, 1, 0)], True)
+    b, _ = rows_of(1, [(band[1][0], 0, None, 0), (band[1][1], None, 2, 1)], True)
+    c, _ = rows_of(2, [(band[2][1], 1, None, 1)], False)
+    assert [bool(r['src']) for r in a] == [False, True] and a[0]['halo'] == band[0][0][0].data_ptr()
+    a_dn = a[1]
+    b_up, b_l0_border, b_l1_border, b_dn = b
+    assert not b_l0_border['src'] and not b_l1_border['src']
+    assert a_dn['src'] == band[0][0][4].data_ptr() and a_dn['halo'] == band[0][0][5].data_ptr()
+    assert a_dn['bytes'] == 8 * 4 * 4 and a_dn['slot_stride'] == slot
+    # A -> B at level 0: A writes B's "from above" pair and counter, B reads exactly those; and the reverse
+    assert a_dn['dst_remote'] == b_up['stage'] and a_dn['flag_remote'] == b_up['flag_local']
+    assert b_up['dst_remote'] == a_dn['stage'] and b_up['flag_remote'] == a_dn['flag_local']
+    assert base[1] <= b_up['stage'] < base[1] + flags_bytes + 32 * slot and base[0] <= a_dn['stage'] < base[1]
+    # B -> C at level 1 uses other slots than level 0
+    (c_up,) = c
+    assert b_dn['dst_remote'] == c_up['stage'] and c_up['dst_remote'] == b_dn['stage']
+    assert b_dn['flag_remote'] == c_up['flag_local'] and c_up['flag_remote'] == b_dn['flag_local']
+    assert len({b_up['stage'], b_dn['stage']}) == 2 and len({b_up['state'], b_dn['state']}) == 2
+    assert abs(b_up['stage'] - b_dn['stage']) >= 2 * slot
+    # a step never spans two launches (neighbours could wait on each other's second launch): 18 rows are refused
+    with pytest.raises(ValueError, match='halo rows in one step'):
+        rows_of(1, [(torch.zeros(4, 2, 4), 0, 2, lv % 8) for lv in range(9)], False)
+    rows, calls = rows_of(1, [(torch.zeros(4, 2, 4), 0, 2, lv) for lv in range(8)], False)
+    assert len(rows) == 16 and calls == 1
+    with pytest.raises(ValueError, match='exceeds the staging slot'):
+        rows_of(1, [(torch.zeros(4, 64, 32), 0, 2, 0)], False)
