@@ -102,6 +102,17 @@ def test_shim_modules_expose_reference_names(lib):
     assert (c.content_weight, c.style_weight, c.tv_weight, c.optimizer, c.levels_num, c.iters_num) == \
            (1e3, 4e5, 1e2, 'lbfgs', 2, 500)
     assert cfg.simultaneous_tasks_count == 2
+    # every field of the reference's Config (config.py:5-30), in its positional order, with its default
+    assert list(vars(c).items()) == [
+        ('content_weight', 1e3), ('style_weight', 4e5), ('tv_weight', 1e2), ('optimizer', 'lbfgs'), ('model', 'vgg19'),
+        ('init_method', 'content+noise'), ('levels_num', 2), ('iters_num', 500), ('noise_factor', 0.95),
+        ('noise_levels', (9, 18, 36, -1, 0)), ('noise_levels_central_amplitude', (0.30, 0.20, 0.10, 0.20, 0.20)),
+        ('noise_levels_peripheral_amplitude', (0.20, 0.30, 0.40, 0.10, 0.00)),
+        ('noise_levels_dispersion', (0.20, 0.30, 0.40, 0.60, 0.30))]
+    c2 = cfg.Config(2.0, optimizer='adam', noise_levels=(-1,))
+    assert (c2.content_weight, c2.style_weight, c2.optimizer, c2.noise_levels) == (2.0, 4e5, 'adam', (-1,))
+    with pytest.raises(TypeError):
+        cfg.Config(no_such_setting=1)
     with pytest.raises(ValueError):
         mu.prepare_model('alexnet', 'cpu')
 
