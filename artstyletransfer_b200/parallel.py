@@ -1,23 +1,23 @@
 """Row-band sharding of the pyramid levels across the GPUs of one box.
 
-Two schemes.  The default (sharded_path.ShardedPathLevel, channels-last feature path) gives every rank exactly its
-band of rows and exchanges ONE halo row with each neighbour before every 3x3 convolution (and the mirrored
-gradient rows in the backward) — no redundant convolution work.  The older scheme below (ShardedLevel, torch
-modules + autograd, used for fp32 precision) pads the band with an 80-row halo instead and crops.
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Every rank holds the full optimizing image and
+an identical optimizer.  The default scheme (sharded_path.ShardedPathLevel on the channels-last feature path):
 
-One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Every rank holds the full optimizing
-image and an identical optimizer.  Per level and closure each rank
-  1. runs VGG19 (torch/cuDNN) on its band of rows plus an 80-row halo on interior sides (the receptive field
-     of relu5_1 is 156 px, so everything inside the band is exact; band edges are multiples of 16 so the four
-     2x2 max-pools never straddle ranks),
-  2. forms the RAW partial Grams F_r F_r^T of its band (the Gram's K dimension is the spatial index, so the
-     full Gram is the plain sum over ranks) and the partial content SSE, straight from the band rows of the
-     NCHW feature maps (pitched TMA loads, no copy),
-  3. joins ONE all-reduce(sum) of the packed buffer [G1 | G2 | G3 | G4 | G5 | content_sse] (~2.4 MB),
-  4. finalizes identically on every rank: 1/(C*HW), minus target, MSE, weighted total,
-and, backward, computes dF_r = s (G - A) F_r for its band only.  The image gradients of all ranks are
-all-reduced once per closure so the replicated optimizers stay bit-identical.  Total variation is evaluated
-on the whole (small) level image by every rank; only rank 0 contributes its gradient.
+  * PyramidBands deals the rows of the WHOLE pyramid out to the ranks (a rank owns a band of one or two levels; at 8
+    ranks the 2048x3072 level sits on six of them and the three lower levels on the other two);
+  * a rank computes exactly its rows and exchanges ONE halo row with each neighbour before every 3x3 convolution
+    (and the mirrored gradient rows in the backward) — no redundant convolution work;
+  * the RAW partial Grams F_r F_r^T of the bands (the Gram's K dimension is the spatial index, so the full Gram is
+    the plain sum over ranks) and the partial content SSE of all levels join ONE all-reduce(sum) of the packed buffer
+    [G1 | G2 | G3 | G4 | G5 | content_sse] per level (~2.4 MB each); every rank finalises identically: 1/(C*HW),
+    minus target, MSE, weighted total; the backward dF_r = s (G - A) F_r is rank-local;
+  * the image gradients of all ranks are all-reduced once per closure so the replicated optimizers stay
+    bit-identical.  Total variation is evaluated on the whole (small) level image by every rank; only rank 0
+    contributes its gradient.
+
+The older scheme (ShardedLevel below: torch modules + autograd around the NCHW kernels, used for fp32 precision)
+cuts every level into `world` equal bands, pads each with an 80-row halo (>= the 78-row receptive-field radius of
+relu5_1) and crops before the Gram — exact, but with redundant convolution work.
 
 The reference has no counterpart (a commented-out two-GPU round-robin, neural_style_transfer.py:238-243).
 """

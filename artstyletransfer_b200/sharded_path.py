@@ -1,17 +1,21 @@
-"""Row-band sharded level on the channels-last feature path, with per-layer halo exchange.
+"""Row-band sharded levels on the channels-last feature path, with per-layer halo exchange.
 
-Every rank owns hb = H / R image rows of the level (hb a multiple of 16, so the four 2x2 max-pools never straddle
-ranks) and ONLY computes those: before each 3x3 convolution it swaps one activation row with each neighbour
-(parallel.halo_exchange; rows are contiguous in NHWC, so they go over NVLink in place, no packing).  The backward
-uses the SAME exchange on the gradient w.r.t. each convolution's output: with the neighbours' edge gradient rows
-in the halos, an ordinary symmetric-padding backward-data convolution over the padded band yields complete
-gradients for the owned rows (its two halo output rows are incomplete and ignored) — cuDNN's asymmetric-padding
-backward-data, which the mirrored "send halo gradients back" scheme needs, runs 1.5x slower on B200.  The first
-convolution needs no exchange in the forward: every rank holds the whole (3-channel) level image.
+A rank owns a band of rows of a level (which rows of which level: parallel.PyramidBands; band edges are multiples of
+16 so the four 2x2 max-pools never straddle ranks; a rank may own nothing of a level) and ONLY computes those:
+before each 3x3 convolution it swaps one activation row with each neighbour (parallel.halo_exchange; rows are
+contiguous in NHWC, so they go over NVLink in place, no packing).  The backward uses the SAME exchange on the
+gradient w.r.t. each convolution's output: with the neighbours' edge gradient rows in the halos, an ordinary
+symmetric-padding backward-data convolution over the padded band yields complete gradients for the owned rows (its
+two halo output rows are incomplete and ignored) — cuDNN's asymmetric-padding backward-data, which the mirrored
+"send halo gradients back" scheme needs, runs 1.5x slower on B200.  The first convolution needs no exchange in the
+forward: every rank holds the whole (3-channel) level image.
 
-Per level and closure: 12 + 12 grouped send/recv steps (<= 0.8 MB each), ONE all-reduce(sum) of the packed raw
-Grams + content SSE (~2.4 MB), then every rank finalises identically.  Activations live in persistent padded
-buffers (row 0 / row h+1 are the halos; at the image border they stay zero = the convolution's zero padding).
+Activations live in padded bands (row 0 / row h+1 are the halos; at the image border they are zero = the
+convolution's zero padding).  The convolutions run as cuDNN's fused conv + bias + ReLU over the whole padded band
+(FUSED_BAND_CONV): the two outer output rows are junk and are exactly the halo rows the next exchange overwrites.
+
+Per closure: 12 + 13 grouped send/recv steps for ALL levels of the rank (<= 0.8 MB per row), ONE all-reduce(sum) of
+the packed raw Grams + content SSE of all levels (~2.4 MB per level), then every rank finalises identically.
 """
 from __future__ import annotations
 
