@@ -183,26 +183,23 @@ def test_halo_exchange_level_matches_unsharded(seeded_vgg, world, H, W):
         assert float(gr[:, :, hi:].abs().max() if hi < H else 0.0) == 0.0
 
 
-@pytest.mark.timeout(300)
-@pytest.mark.parametrize('world,bands,n_levels', [(2, 'uniform', 2), (4, 'uniform', 2), (2, 'pyramid', 3),
-                                                  (3, 'pyramid', 3), (4, 'pyramid', 3), (8, 'pyramid', 3)])
-def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, world, bands, n_levels):
-    """The pyramid levels evaluated in lock-step with grouped halo exchanges == the unsharded closure (bicubic chain
-    + every level + backward), summed over the emulated ranks.  'uniform': every level cut into `world` equal bands;
-    'pyramid': the level-aware plan (parallel.PyramidBands) — unequal bands, ranks that own rows of two levels, ranks
-    that own nothing of a level and are skipped by their neighbours' exchange."""
+def run_lockstep(world, bands, n_levels, weights=WEIGHTS, content_idx=None, hw=None):
+    """The unsharded closure (bicubic chain + every level + backward) and the same closure on `world` emulated ranks
+    in lock-step.  Returns a dict: ref_total, ref_grad, totals (per rank), grads (per rank), plan, inputs."""
     from artstyletransfer_b200 import math_utils, neural_style_transfer as nst, ops
     from artstyletransfer_b200.parallel import PyramidBands
     from artstyletransfer_b200.sharded_path import PyramidFn, ShardedPathLevel, ShardedPyramid
-    H, W = (256, 96) if n_levels == 2 else (256, 128)
+    H, W = hw or ((256, 96) if n_levels == 2 else (256, 128))
     content, style = O.synthetic_images(H, W, seed=11)
     init = np.clip(content * 0.5 + np.random.default_rng(12).uniform(0, 1, size=content.shape) * 0.5, 0, 1).astype(np.float32)
     net, cidx, sidx = math_utils.prepare_model('vgg19', dev())
+    if content_idx is not None:
+        cidx = content_idx
     c_lv = [content[::1 << i, ::1 << i].copy() for i in range(n_levels)]
     s_lv = [style[::1 << i, ::1 << i].copy() for i in range(n_levels)]
     c_img = [nst.prepare_img(c, dev()) for c in c_lv]
     s_img = [nst.prepare_img(s_, dev()) for s_ in s_lv]
-    lbs = [nst.LossBuilder(cidx, sidx, c, s_, net, *WEIGHTS) for c, s_ in zip(c_img, s_img)]
+    lbs = [nst.LossBuilder(cidx, sidx, c, s_, net, *weights) for c, s_ in zip(c_img, s_img)]
     img = nst.prepare_img(init, dev()).requires_grad_(True)
     lv, total = img, None
     for i in range(n_levels):
@@ -215,8 +212,6 @@ def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, world, bands, n_
     plan = lbs[0].path_plan(img)
     sizes = [(H >> i, W >> i) for i in range(n_levels)]
     pb = PyramidBands(sizes, world, uniform=bands == 'uniform')
-    if bands == 'pyramid' and world > 2:           # the plan really is heterogeneous at these sizes
-        assert any(pb.band(li, r)[0] == pb.band(li, r)[1] for li in range(n_levels) for r in range(world))
 
     shared = {'bufs': [None] * world, 'barrier': threading.Barrier(world, timeout=60), 'mail': {}}
     results = [None] * world
@@ -229,7 +224,7 @@ def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, world, bands, n_
         try:
             torch.cuda.set_device(dev())
             grp = ThreadGroup(rank, world, shared)
-            levels = [ShardedPathLevel(grp, plan, c_img[i], s_img[i], cidx, sidx, WEIGHTS, *sizes[i],
+            levels = [ShardedPathLevel(grp, plan, c_img[i], s_img[i], cidx, sidx, weights, *sizes[i],
                                        band=(*pb.band(i, rank), *pb.neighbours(i, rank))) for i in range(n_levels)]
             pyr = ShardedPyramid(levels)
             out = []
@@ -251,12 +246,96 @@ def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, world, bands, n_
     [t.start() for t in threads]
     [t.join() for t in threads]
     assert not errors, root_causes(errors)
+    return {'ref_total': ref_total, 'ref_grad': ref_grad, 'totals': [r[0] for r in results],
+            'grads': [r[1] for r in results], 'plan': pb, 'sizes': sizes, 'init': init, 'c_lv': c_lv, 's_lv': s_lv,
+            'cidx': cidx, 'sidx': sidx}
+
+
+def fp64_closure_grad(run, weights):
+    """The oracle's torch closure in float64 on the device: the 'true' gradient both TF32 paths approximate."""
+    onet, _, _ = O.make_vgg19(1234)
+    onet = onet.to(dev()).double()
+    targets = [O.torch_targets(onet, run['cidx'], run['sidx'], torch.from_numpy(O.prepare_img(c)).to(dev()).double(),
+                               torch.from_numpy(O.prepare_img(s)).to(dev()).double())
+               for c, s in zip(run['c_lv'], run['s_lv'])]
+    _, _, g = O.torch_closure(onet, run['cidx'], run['sidx'], targets,
+                              torch.from_numpy(O.prepare_img(run['init'])).to(dev()).double(), weights)
+    return g
+
+
+def row_error_profile(diff, ref):
+    """Per image row r of the top level: ||diff[..., r, :]|| / rms over rows of ||ref[..., r, :]||."""
+    d = torch.linalg.norm(diff.double().permute(2, 0, 1, 3).reshape(diff.shape[2], -1), dim=1)
+    n = torch.linalg.norm(ref.double().permute(2, 0, 1, 3).reshape(ref.shape[2], -1), dim=1)
+    return (d / n.pow(2).mean().sqrt()).cpu().numpy()
+
+
+LOCKSTEP_CASES = [(2, 'uniform', 2), (4, 'uniform', 2), (2, 'pyramid', 3), (3, 'pyramid', 3), (4, 'pyramid', 3),
+                  (8, 'pyramid', 3)]
+# TF32 Gram operands: the same image-gradient budget as the unsharded closure (tests/test_gpu_closure.py)
+GRAD_BUDGET_TF32 = 2e-3
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('world,bands,n_levels', LOCKSTEP_CASES)
+def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, world, bands, n_levels):
+    """The pyramid levels evaluated in lock-step with grouped halo exchanges == the unsharded closure (bicubic chain
+    + every level + backward), summed over the emulated ranks.  'uniform': every level cut into `world` equal bands;
+    'pyramid': the level-aware plan (parallel.PyramidBands) — unequal bands, ranks that own rows of two levels, ranks
+    that own nothing of a level and are skipped by their neighbours' exchange.
+
+    Tolerance.  Nothing in the band scheme is approximate (test_lockstep_pyramid_is_exact_without_gram_noise below
+    shows 1e-5 agreement once the TF32 Gram is out of the loss), but the two paths round DIFFERENT values: the Gram
+    is a sum over positions, its split-K order differs between one 148-CTA launch and per-band launches + all-reduce,
+    D = G - A is ~1e-2 of G (cancellation), and D is then rounded to TF32 (2^-11) as the backward's operand — a
+    1-ulp fp32 difference in G flips TF32 roundings of D.  So sharded-vs-unsharded is bounded by the TF32 noise of
+    EACH against the true (float64) gradient, not by a number tuned on one box:
+      * both paths are within the TF32 gradient budget (2e-3) of the float64 oracle gradient;
+      * the sharded path is no further from it than the unsharded one (x1.5 + 1e-4 slack);
+      * the difference is not concentrated at band edges (a halo bug would be): rows within 2 of a band edge of the
+        top level carry no more error than 3x the typical row."""
+    from artstyletransfer_b200.parallel import PyramidBands  # noqa: F401
+    run = run_lockstep(world, bands, n_levels)
+    pb, ref_total, ref_grad = run['plan'], run['ref_total'], run['ref_grad']
+    if bands == 'pyramid' and world > 2:           # the plan really is heterogeneous at these sizes
+        assert any(pb.band(li, r)[0] == pb.band(li, r)[1] for li in range(n_levels) for r in range(world))
     for r in range(world):
-        assert abs(results[r][0] - ref_total) <= 1e-4 * abs(ref_total)
-        assert results[r][0] == results[0][0]
-    gsum = sum(results[r][1] for r in range(world))
+        assert abs(run['totals'][r] - ref_total) <= 1e-4 * abs(ref_total)
+        assert run['totals'][r] == run['totals'][0]
+    gsum = sum(run['grads'])
+    g64 = fp64_closure_grad(run, WEIGHTS)
+    n64 = torch.linalg.norm(g64)
+    e_un = float(torch.linalg.norm(ref_grad.double() - g64) / n64)
+    e_sh = float(torch.linalg.norm(gsum.double() - g64) / n64)
     gerr = float(torch.linalg.norm(gsum - ref_grad) / torch.linalg.norm(ref_grad))
-    assert gerr < 5e-4, gerr
+    prof = row_error_profile(gsum - ref_grad, ref_grad)
+    edges = sorted({e for e in pb.bounds[0][1:-1] if 0 < e < run['sizes'][0][0]})
+    near = sorted({r for e in edges for r in range(e - 2, e + 2)})
+    typical = float(np.median(prof))
+    worst_edge = float(prof[near].max()) if near else 0.0
+    print(f'lockstep[{world}-{bands}-{n_levels}] sharded-vs-unsharded={gerr:.3e} unsharded-vs-fp64={e_un:.3e} '
+          f'sharded-vs-fp64={e_sh:.3e} row error: median={typical:.3e} max={prof.max():.3e} at band edges {edges}: '
+          f'{worst_edge:.3e}')
+    assert e_un < GRAD_BUDGET_TF32 and e_sh < GRAD_BUDGET_TF32, (e_un, e_sh)
+    assert e_sh <= 1.5 * e_un + 1e-4, (e_sh, e_un)
+    assert gerr <= e_un + e_sh + 1e-6, (gerr, e_un, e_sh)           # triangle inequality: a sanity check of the probe
+    assert worst_edge <= 3.0 * typical + 1e-6, (worst_edge, typical, edges)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('world,bands,n_levels', [(2, 'pyramid', 3), (4, 'pyramid', 3), (4, 'uniform', 2)])
+def test_lockstep_pyramid_is_exact_without_gram_noise(seeded_vgg, world, bands, n_levels):
+    """Style weight 0 and the content term moved to the deepest tap (relu5_1): the gradient then flows through every
+    convolution, pool, halo exchange and the bicubic chain but through no TF32 Gram, so the sharded closure must
+    reproduce the unsharded one to fp32 summation order (convolutions are fp32-exact in this module)."""
+    weights = (1e3, 0.0, 1e2)
+    run = run_lockstep(world, bands, n_levels, weights=weights, content_idx=5)
+    for r in range(world):
+        assert abs(run['totals'][r] - run['ref_total']) <= 2e-6 * abs(run['ref_total'])
+    gsum = sum(run['grads'])
+    gerr = float(torch.linalg.norm(gsum - run['ref_grad']) / torch.linalg.norm(run['ref_grad']))
+    print(f'exact[{world}-{bands}-{n_levels}] sharded-vs-unsharded={gerr:.3e}')
+    assert gerr < 5e-5, gerr
 
 
 def test_band_plan_and_pack_layout():
