@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libast_sm100.so')
 
-AST_ABI_VERSION = 3
+AST_ABI_VERSION = 4
 AST_PREC_TF32, AST_PREC_FP32 = 0, 1
 AST_LAYOUT_CHW, AST_LAYOUT_HWC = 0, 1
 AST_COORD_TORCH, AST_COORD_CV2 = 0, 1
@@ -60,6 +60,7 @@ SIGNATURES = {
     'ast_maxpool2x2_bwd_nhwc': (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     'ast_chw_to_hwc': (_i, [_p, _i, _i64, _i64, _p, _p]),
     'ast_hwc_to_chw': (_i, [_p, _i, _i64, _p, _i64, _i, _p]),
+    'ast_unprepare_hwc': (_i, [_p, _i64, _d, _d, _d, _p, _p]),
     'ast_tv_fwd': (_i, [_p, _i, _i, _i, _p, _p, _p, _sz, _p]),
     'ast_tv_bwd': (_i, [_p, _i, _i, _i, _p, _f, _f, _p, _p, _i, _p]),
     'ast_level_combine': (_i, [_p, _i, _p, _p, _f, _f, _f, _p, _p]),

@@ -175,6 +175,34 @@ __global__ void __launch_bounds__(kGlueThreads) hwc_to_chw_kernel(const float* _
   }
 }
 
+// unprepare_img (neural_style_transfer.py:388-393 of the reference) on the device: planar (3, H*W) "x*255 - mean"
+// image -> interleaved (H*W, 3) in [0,1].  The reference adds a float64 mean to the float32 array in place (numpy
+// computes the sum in double and rounds to float), then divides the float32 array by 255: y = fl32(fl32(x + mean) / 255).
+// Four pixels per thread: three coalesced 16-byte plane loads, three 16-byte stores of the 12 interleaved floats.
+__global__ void __launch_bounds__(kGlueThreads) unprepare_hwc_kernel(const float* __restrict__ x, int64_t HW, double m0,
+                                                                    double m1, double m2, float* __restrict__ y) {
+  const int64_t n4 = HW >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = ldg_stream(reinterpret_cast<const float4*>(x) + i);
+    const float4 b = ldg_stream(reinterpret_cast<const float4*>(x + HW) + i);
+    const float4 c = ldg_stream(reinterpret_cast<const float4*>(x + 2 * HW) + i);
+#define AST_UNPREP(v, m) ((float)((double)(v) + (m)) / 255.0f)
+    float4* o = reinterpret_cast<float4*>(y) + 3 * i;
+    stg_stream(o, make_float4(AST_UNPREP(a.x, m0), AST_UNPREP(b.x, m1), AST_UNPREP(c.x, m2), AST_UNPREP(a.y, m0)));
+    stg_stream(o + 1, make_float4(AST_UNPREP(b.y, m1), AST_UNPREP(c.y, m2), AST_UNPREP(a.z, m0), AST_UNPREP(b.z, m1)));
+    stg_stream(o + 2, make_float4(AST_UNPREP(c.z, m2), AST_UNPREP(a.w, m0), AST_UNPREP(b.w, m1), AST_UNPREP(c.w, m2)));
+  }
+  // tail pixels (HW % 4) by the first threads of block 0
+  if (blockIdx.x == 0 && threadIdx.x < (HW & 3)) {
+    const int64_t p = (n4 << 2) + threadIdx.x;
+    y[3 * p] = AST_UNPREP(x[p], m0);
+    y[3 * p + 1] = AST_UNPREP(x[HW + p], m1);
+    y[3 * p + 2] = AST_UNPREP(x[2 * HW + p], m2);
+  }
+#undef AST_UNPREP
+}
+
 }  // namespace ast
 
 using namespace ast;
@@ -240,4 +268,14 @@ extern "C" int ast_hwc_to_chw(const float* x, int C, int64_t HW, float* y, int64
   hwc_to_chw_kernel<<<glue_grid(HW * C), kGlueThreads, 0, (cudaStream_t)stream>>>(x, C, HW, plane_stride, y,
                                                                                  accumulate ? 1 : 0);
   return check_launch("hwc_to_chw");
+}
+
+extern "C" int ast_unprepare_hwc(const float* x_chw, int64_t HW, double mean0, double mean1, double mean2, float* y_hwc,
+                                 void* stream) {
+  AST_REQUIRE(x_chw && y_hwc, AST_ERR_INVALID, "ast_unprepare_hwc: null pointer");
+  AST_REQUIRE(HW > 0 && HW % 4 == 0, AST_ERR_INVALID, "ast_unprepare_hwc: H*W must be a positive multiple of 4 (got %lld)",
+              (long long)HW);
+  AST_REQUIRE(al16(x_chw) && al16(y_hwc), AST_ERR_INVALID, "ast_unprepare_hwc: pointers must be 16-byte aligned");
+  unprepare_hwc_kernel<<<glue_grid(HW / 4), kGlueThreads, 0, (cudaStream_t)stream>>>(x_chw, HW, mean0, mean1, mean2, y_hwc);
+  return check_launch("unprepare_hwc");
 }

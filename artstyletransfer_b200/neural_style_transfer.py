@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import asyncio
 import os
+import threading
 import traceback
 
 import numpy as np
@@ -48,8 +49,26 @@ CHANNELS_LAST_PATH = os.environ.get('AST_CHANNELS_LAST', '1') != '0'
 # replayed: a closure is ~1 000 launches, and at the small pyramid levels (and on row bands) the host cannot
 # issue them as fast as the GPU retires them.
 GRAPH_CLOSURE = os.environ.get('AST_CUDA_GRAPH', '1') != '0'
+# A failed capture normally falls back to eager launches (a feature net that synchronises cannot be captured).
+# When the graph was asked for explicitly (AST_CUDA_GRAPH=1 in the environment, or AST_CUDA_GRAPH_STRICT=1, or
+# bench.py) the failure is raised instead: a silently eager run is only visible as a slower number.
+GRAPH_STRICT = os.environ.get('AST_CUDA_GRAPH') == '1' or os.environ.get('AST_CUDA_GRAPH_STRICT', '0') == '1'
 GRAPH_WARMUP = 2
 FUSED_ADAM = os.environ.get('AST_FUSED_ADAM', '1') != '0'
+# True: process() takes the per-step image snapshot (:207-208) off the critical path — one fused unprepare kernel into
+# a device staging buffer, the device->host copy on a side stream into page-locked memory, and the NEXT optimizer
+# step is enqueued before the copy is awaited, so the GPU never idles on the yield.  The sequence of yielded
+# (image, step) pairs is the reference's.  False: snapshot, copy and wait before the next step starts.
+ASYNC_YIELD = os.environ.get('AST_ASYNC_YIELD', '1') != '0'
+# Row-band sharding: every rank runs the same loop and holds the same image; only rank 0 copies it to the host
+# (the other ranks yield None for the image) unless this is set.
+YIELD_ON_ALL_RANKS = os.environ.get('AST_YIELD_ALL_RANKS', '0') == '1'
+
+# The reference runs up to simultaneous_tasks_count = 2 jobs in one process (config.py:1, task_executor.py:9): their
+# closures come from different executor threads and their set-up / yields from the event-loop thread.  A CUDA-graph
+# capture must not overlap another thread's cudaMalloc / cudaHostAlloc, so captures use thread-local capture mode AND
+# are serialised against the allocation-heavy helpers (job set-up, init image, resize, the yield's pinned block).
+_GPU_SETUP_LOCK = threading.RLock()
 
 
 class ContentStylePair:
@@ -171,6 +190,12 @@ class _Job:
                                f'got device {device} (no CPU fallback)')
         if optimizer_name not in ('adam', 'lbfgs'):
             raise RuntimeError("Unknown optimizer")
+        with _GPU_SETUP_LOCK:
+            self._setup(device, model_name, style_imgs, optimizer_name, content_imgs, init_img, lr_start,
+                        content_weight, style_weight, tv_weight, init_img_name)
+
+    def _setup(self, device, model_name, style_imgs, optimizer_name, content_imgs, init_img, lr_start,
+               content_weight, style_weight, tv_weight, init_img_name):
         neural_net, content_feature_maps_index, style_feature_maps_indices = \
             math_utils.prepare_model(model_name, device)
         if VERBOSE:
@@ -245,16 +270,18 @@ class _Job:
         """Capture one closure into a CUDA graph.  The image leaf is updated in place by Adam / LBFGS, so its
         storage is the graph's static input; the summed loss and the image gradient are its static outputs."""
         dev = self.optimizing_img.device
-        self.optimizing_img.grad = None          # backward() inside the capture creates .grad in the graph's pool
-        torch.cuda.synchronize(dev)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            total = self._evaluate()
-        static_total = total.detach()
-        static_grad = self.optimizing_img.grad
-        if static_grad is None:
-            raise RuntimeError('closure capture produced no image gradient')
-        self._graph = (graph, static_total, static_grad)
+        with _GPU_SETUP_LOCK:                    # no other job sets up / captures while this capture is open
+            self.optimizing_img.grad = None      # backward() inside the capture creates .grad in the graph's pool
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            # thread_local: another job's executor thread may still allocate (its eager closures) during the capture
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                total = self._evaluate()
+            static_total = total.detach()
+            static_grad = self.optimizing_img.grad
+            if static_grad is None:
+                raise RuntimeError('closure capture produced no image gradient')
+            self._graph = (graph, static_total, static_grad)
 
     def closure(self):
         try:
@@ -275,7 +302,7 @@ class _Job:
                     self._graph_failed = True
                     self._graph = None
                     optimizing_img.grad = None
-                    if os.environ.get('AST_CUDA_GRAPH_STRICT', '0') == '1':
+                    if GRAPH_STRICT:
                         raise
                     traceback.print_exc()
             if self._graph is not None and torch.is_grad_enabled() and not ops.STATS.enabled and not VERBOSE:
@@ -313,10 +340,92 @@ class NeuralStyleTransfer:
                       init_img_name):
         job = _Job(self.__device, self.__model_name, self.__style_imgs, self.__optimizer_name, content_imgs, init_img,
                    lr_start, content_weight, style_weight, tv_weight, init_img_name)
-        # the main optimization loop (:205-208): optimizer.step runs on the default executor's worker thread
-        while job.step < iters_num:
-            await asyncio.get_running_loop().run_in_executor(None, job.optimizer_step)
-            yield unprepare_img(job.optimizing_img), job.step
+        loop = asyncio.get_running_loop()
+        if not ASYNC_YIELD:
+            # the main optimization loop (:205-208): optimizer.step runs on the default executor's worker thread
+            while job.step < iters_num:
+                await loop.run_in_executor(None, job.optimizer_step)
+                yield unprepare_img(job.optimizing_img), job.step
+            return
+        # Same loop, same (image, step) sequence, with the yield overlapped: after step k has been enqueued its image
+        # is snapshotted on the device (in stream order, before step k+1 can touch it), step k+1 is handed to the
+        # executor, and only then is the snapshot's device->host copy awaited and yielded.
+        yielder = _ImageYielder(job.optimizing_img)
+        pending = loop.run_in_executor(None, job.optimizer_step) if job.step < iters_num else None
+        try:
+            while pending is not None:
+                fut, pending = pending, None
+                await fut
+                step = job.step
+                ticket = yielder.begin()
+                if step < iters_num:
+                    pending = loop.run_in_executor(None, job.optimizer_step)
+                img = await loop.run_in_executor(None, yielder.finish, ticket)
+                yield img, step
+        finally:
+            if pending is not None:          # the consumer stopped early: let the step in flight finish quietly
+                try:
+                    await pending
+                except Exception:
+                    pass
+
+
+class _ImageYielder:
+    """The per-step image yield of process() (:207-208: deepcopy, unprepare_img, device->host) off the critical path.
+    begin() — called between two optimizer steps — enqueues ONE kernel on the current stream that writes the
+    unprepared (H, W, 3) [0,1] image into one of two device staging buffers (that is the snapshot: the next step may
+    overwrite the leaf as soon as it has run), and the device->host copy into a fresh page-locked block on a side
+    stream.  finish() waits for that copy only.  Under row-band sharding every rank holds the same image; rank 0
+    alone copies (YIELD_ON_ALL_RANKS restores the copy everywhere), the others yield None."""
+
+    def __init__(self, optimizing_img: Tensor):
+        self.img = optimizing_img
+        dev = optimizing_img.device
+        _, c, h, w = optimizing_img.shape
+        rank, world = _parallel.world()
+        self.active = YIELD_ON_ALL_RANKS or world == 1 or rank == 0
+        self.fused = c == 3 and (h * w) % 4 == 0 and optimizing_img.is_contiguous()
+        self.shape = (h, w, c)
+        self.n = 0
+        if self.active:
+            with _GPU_SETUP_LOCK:
+                self.stage = [torch.empty(self.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+                self.side = torch.cuda.Stream(dev)
+            self.drained = [None, None]      # event: the copy that last read stage[i] has finished
+
+    def begin(self):
+        if not self.active:
+            return None
+        dev = self.img.device
+        i = self.n & 1
+        self.n += 1
+        main = torch.cuda.current_stream(dev)
+        if self.drained[i] is not None:
+            main.wait_event(self.drained[i])
+        if self.fused:
+            ops.unprepare_hwc(self.img.detach(), self.stage[i], IMAGENET_MEAN_255)
+        else:
+            mean = torch.tensor(IMAGENET_MEAN_255, dtype=torch.float32, device=dev).view(1, 3, 1, 1)
+            self.stage[i].copy_(((self.img.detach() + mean) / 255).permute([0, 2, 3, 1]).squeeze(0))
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with _GPU_SETUP_LOCK:                # a pinned block may be a fresh cudaHostAlloc: not during a capture
+            host = torch.empty(self.shape, dtype=torch.float32, pin_memory=True)
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            host.copy_(self.stage[i], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        self.drained[i] = done
+        return host, done
+
+    @staticmethod
+    def finish(ticket):
+        if ticket is None:
+            return None
+        host, done = ticket
+        done.synchronize()
+        return host.numpy()
 
 
 def _device():
@@ -347,10 +456,11 @@ async def resize(img, level):
     Same result as cv2.resize(..., INTER_CUBIC) on float32 images, computed by the K6 kernel. """
     new_height, new_width = level_size(img, level)
     dev = _device()
-    src = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32)).to(dev)
-    if src.dim() == 2:
-        src = src.unsqueeze(-1)
-    out = _resize_hwc_device(src, new_height, new_width).cpu().numpy()
+    with _GPU_SETUP_LOCK:
+        src = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32)).to(dev)
+        if src.dim() == 2:
+            src = src.unsqueeze(-1)
+        out = _resize_hwc_device(src, new_height, new_width).cpu().numpy()
     return out if img.ndim == 3 else out[:, :, 0]
 
 
@@ -372,9 +482,10 @@ async def neural_style_transfer(content_n_style: ContentStylePair,
         content_img_levels.insert(0, await resize(content_n_style.content[1], level=level))
         style_img_levels.insert(0, await resize(content_n_style.style[1], level=level))
 
-    init_img_next, init_img_name = build_init_image(
-        content_n_style, content_img_levels, style_img_levels, init_method, noise_factor, noise_levels,
-        noise_levels_central_amplitude, noise_levels_peripheral_amplitude, noise_levels_dispersion, device)
+    with _GPU_SETUP_LOCK:
+        init_img_next, init_img_name = build_init_image(
+            content_n_style, content_img_levels, style_img_levels, init_method, noise_factor, noise_levels,
+            noise_levels_central_amplitude, noise_levels_peripheral_amplitude, noise_levels_dispersion, device)
 
     nst = NeuralStyleTransfer(device, model_name, style_img_levels, optimizer_name)
     lr_start = 10.0
@@ -496,12 +607,18 @@ def unprepare_img(img: Tensor):
     """ Reverse of prepare_img (:388-393): (1,3,H,W) tensor -> HxWx3 float32 numpy on the host.
     The mean add and the /255 run on the device, then ONE contiguous device->host copy of the HWC image. """
     t = img.detach()
-    mean = torch.tensor(IMAGENET_MEAN_255, dtype=torch.float32, device=t.device).view(1, 3, 1, 1)
-    hwc = ((t + mean) / 255).permute([0, 2, 3, 1]).squeeze(0).contiguous()
+    if t.is_cuda and t.dim() == 4 and t.shape[0] == 1 and t.shape[1] == 3 and (t.shape[2] * t.shape[3]) % 4 == 0 \
+            and t.dtype == torch.float32 and t.is_contiguous():
+        hwc = torch.empty((t.shape[2], t.shape[3], 3), dtype=torch.float32, device=t.device)
+        ops.unprepare_hwc(t, hwc, IMAGENET_MEAN_255)
+    else:
+        mean = torch.tensor(IMAGENET_MEAN_255, dtype=torch.float32, device=t.device).view(1, 3, 1, 1)
+        hwc = ((t + mean) / 255).permute([0, 2, 3, 1]).squeeze(0).contiguous()
     if not hwc.is_cuda:
         return hwc.numpy()
     # fresh page-locked block from torch's caching host allocator (recycled once the caller drops the array)
-    host = torch.empty(hwc.shape, dtype=torch.float32, pin_memory=True)
+    with _GPU_SETUP_LOCK:
+        host = torch.empty(hwc.shape, dtype=torch.float32, pin_memory=True)
     host.copy_(hwc, non_blocking=True)
     torch.cuda.current_stream(hwc.device).synchronize()
     return host.numpy()

@@ -71,7 +71,7 @@ _KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_mse_fwd_nhwc': 2, 'ast_gra
                      'ast_tv_fwd': 1, 'ast_tv_bwd': 1, 'ast_level_combine': 1, 'ast_bicubic_down2x': 1,
                      'ast_bicubic_down2x_adj': 1, 'ast_bicubic_resize': 1, 'ast_bicubic_resize_adj': 1,
                      'ast_noise_init': 1, 'ast_bias_relu_nhwc': 1, 'ast_relu_bwd': 1, 'ast_maxpool2x2_nhwc': 1,
-                     'ast_maxpool2x2_bwd_nhwc': 1, 'ast_chw_to_hwc': 1, 'ast_hwc_to_chw': 1, 'ast_halo_exchange': 1}
+                     'ast_maxpool2x2_bwd_nhwc': 1, 'ast_chw_to_hwc': 1, 'ast_hwc_to_chw': 1, 'ast_unprepare_hwc': 1, 'ast_halo_exchange': 1}
 
 
 def _launch(dev: torch.device, key, name: str, *args) -> None:
@@ -271,6 +271,13 @@ def hwc_to_chw(x: torch.Tensor, y: torch.Tensor, c: int, hw: int, accumulate: bo
                x_off: int = 0, y_off: int = 0) -> None:
     _launch(x.device, ('hwc_to_chw', c, hw), 'ast_hwc_to_chw', x.data_ptr() + 4 * x_off, c, hw,
             y.data_ptr() + 4 * y_off, hw if plane is None else plane, int(accumulate))
+
+
+def unprepare_hwc(x: torch.Tensor, y: torch.Tensor, mean) -> None:
+    """(1,3,H,W) planar 'x*255 - mean' image -> (H,W,3) in [0,1] (neural_style_transfer.py:388-393), one pass."""
+    hw = x.shape[-2] * x.shape[-1]
+    _launch(x.device, ('unprepare', hw), 'ast_unprepare_hwc', x.data_ptr(), hw, float(mean[0]), float(mean[1]),
+            float(mean[2]), y.data_ptr())
 
 
 # ------------------------------------------------------------------------------------------------------

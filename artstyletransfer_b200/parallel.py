@@ -57,6 +57,9 @@ class BandPlan:
         return self.r0 // stride, self.r1 // stride
 
 
+# how the halo rows of a lock-step step travel: 'nccl' = one grouped send/recv, 'peer' = one ast_halo_exchange launch
+# over NVLink peer memory (PeerHaloGroup)
+DEFAULT_HALO = 'nccl'
 BAND_OVERHEAD = float(os.environ.get('AST_BAND_OVERHEAD', '0.015'))
 MIN_BAND_ROWS = 2 * ALIGN
 
@@ -365,7 +368,7 @@ def init_sharding(group=None) -> None:
     if group is None:
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError('init_sharding() needs an initialized torch.distributed process group')
-        group = PeerHaloGroup() if os.environ.get('AST_HALO', 'nccl') == 'peer' else TorchDistGroup()
+        group = PeerHaloGroup() if os.environ.get('AST_HALO', DEFAULT_HALO) == 'peer' else TorchDistGroup()
     _GROUP = group
 
 

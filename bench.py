@@ -33,6 +33,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = 'pyramid_L3_optim_steps_per_s'
+
+
+def metric_name(levels):
+    return METRIC if levels == LEVELS else f'pyramid_L{levels - 1}_optim_steps_per_s'
 UNIT = 'steps/s'
 LEVELS = 4
 WEIGHTS = (1e3, 4e5, 1e2)
@@ -54,6 +58,11 @@ def parse():
                     help='leave cuDNN on its heuristics (default: time its engines once per convolution shape)')
     ap.add_argument('--profile', default=None, help='write a torch.profiler kernel table of 3 timed-mode steps (rank 0) to this path')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-library-baseline', action='store_true',
+                    help='skip the torch/cuDNN/cuBLAS "library bar" (the reference closure with device=cuda) at N=1')
+    ap.add_argument('--cpu-budget-s', type=float, default=480.0,
+                    help='--impl reference: wall-clock budget for warmup+steps of the REAL config; above it the '
+                         'steps fall back to a bounded sample and the line says so')
     return ap.parse_args()
 
 
@@ -187,6 +196,16 @@ def kernel_work(key):
         return 4.0 * c * (2 * h * w + (h // 2) * (w // 2)), 0.0
     if k in ('chw_to_hwc', 'hwc_to_chw'):
         return 8.0 * key[1] * key[2], 0.0
+    if k == 'unprepare':
+        return 24.0 * key[1], 0.0           # 3 planes read, 3 interleaved channels written
+    if k == 'noise_init':
+        return 24.0 * key[1] * key[2], 0.0  # K7: content read once, init written once
+    if k == 'resize':
+        _, c, h, w, oh, ow = key
+        return 4.0 * c * (h * w + oh * ow), 0.0
+    if k in ('down2x_tv', 'down2x_adj_tv'):
+        _, c, h, w = key
+        return 4.0 * c * (h * w + h * w / 4), 0.0
     return 0.0, 0.0
 
 
@@ -236,6 +255,23 @@ def phase(msg):
         print(f'[bench +{time.perf_counter() - _T0:7.1f}s] {msg}', file=sys.stderr, flush=True)
 
 
+INIT_ARGS = ('content+noise', 0.95, (9, 18, 36, -1, 0), (0.30, 0.20, 0.10, 0.20, 0.20), (0.20, 0.30, 0.40, 0.10, 0.00),
+             (0.20, 0.30, 0.40, 0.60, 0.30))          # config.Config() defaults (config.py:10-18)
+
+
+def workload_config(args):
+    """The workload, stated identically by both arms (--impl ours / reference): same images, weights, optimizer,
+    init and step definition.  Arm-specific facts (sharding, graphs, sampling) live in 'impl_config'."""
+    H, W = 256 * 2 ** (args.levels - 1), 384 * 2 ** (args.levels - 1)
+    cfg_no = {1: 0, 2: 1, 3: 2, 4: 3}.get(args.levels)
+    return {'workload': f'L={args.levels - 1} {args.levels}-level pyramid {H}x{W}, random-init VGG19 seed 1234, '
+                        f'{args.optimizer}, structured-noise init (BASELINE configs[{cfg_no}])',
+            'levels': args.levels, 'image': [H, W], 'optimizer': args.optimizer,
+            'weights': list(WEIGHTS), 'init': 'content+noise, Config() noise levels (9,18,36,-1,0), np.random.seed(0)',
+            'step': 'one optimizer.step = Adam: 1 closure (all levels fwd+bwd) + update; LBFGS: 2 closures',
+            'cache': 'working set of a step (>= 1 GB of activations at every level set) >> 126 MB L2: no flush needed'}
+
+
 def build_job(args, dev):
     """Images, init and the _Job (leaf image + optimizer + per-level LossBuilders), as process() builds them."""
     import numpy as np
@@ -249,9 +285,7 @@ def build_job(args, dev):
     pair = nst.ContentStylePair(('synthetic-content', content_src), ('synthetic-style', style_src))
     np.random.seed(0)
     t0 = time.perf_counter()
-    init, name = nst.build_init_image(pair, content_levels, style_levels, 'content+noise', 0.95, (9, 18, 36, -1, 0),
-                                      (0.30, 0.20, 0.10, 0.20, 0.20), (0.20, 0.30, 0.40, 0.10, 0.00),
-                                      (0.20, 0.30, 0.40, 0.60, 0.30), dev)
+    init, name = nst.build_init_image(pair, content_levels, style_levels, *INIT_ARGS, dev)
     torch.cuda.synchronize()
     init_s = time.perf_counter() - t0
     return content_levels, style_levels, init, name, init_s
@@ -272,16 +306,25 @@ def run_ours(args):
     if args.precision:
         nst.PRECISION = args.precision
     from artstyletransfer_b200 import feature_path
-    feature_path.CUDNN_BENCHMARK = not args.no_cudnn_autotune
+    if args.no_cudnn_autotune:        # product default: on (feature_path.CUDNN_BENCHMARK); off for runs under ncu
+        feature_path.CUDNN_BENCHMARK = False
+    nst.GRAPH_STRICT = True           # a failed capture must fail the bench, not show up as a slower number
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
         parallel.init_sharding()
     seeded_vgg_patch()
     phase('library loaded')
+    build_job(args, dev)              # untimed first pass: allocator / module warm-up of the set-up path
+    ops.STATS.reset(enabled=True, timing=True)
     content_levels, style_levels, init, name, init_s = build_job(args, dev)
+    torch.cuda.synchronize()
+    setup_kernels = ops.STATS.summary()
+    ops.STATS.reset(enabled=False)
     H, W = init.shape[0], init.shape[1]
     phase('images + init built')
     job = nst._Job(dev, 'vgg19', style_levels, args.optimizer, content_levels, init, 10.0, *WEIGHTS, name)
+    # parity across N: the first closure sees the same image on every rank count, so its loss and gradient must agree
+    parity = first_closure_parity(job, rank, dev)
 
     def barrier():
         if world > 1:
@@ -345,7 +388,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = closures / (ms * 1e-3)
-    loss_now = float(job.closure().item()) if rank == 0 and world == 1 else None
+    loss_now = float(job.closure().item())          # collective under sharding: every rank evaluates
     mem_gb = torch.cuda.max_memory_allocated(dev) / 1e9
 
     # ---- end to end through the public API ---------------------------------------------------------------
@@ -380,10 +423,12 @@ def run_ours(args):
             t = torch.tensor([wall], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             wall = float(t.item())
-        assert img.shape == (H, W, 3) and img.dtype == np.float32
+        if rank == 0:
+            assert img.shape == (H, W, 3) and img.dtype == np.float32
         e2e = {'value': (step1 - step0) / wall, 'unit': UNIT, 'h2d_bytes_per_step': 0,
-               'd2h_bytes_per_step': int(img.nbytes), 'timed': 'wall clock around K optimizer steps incl. the per-step '
-               'image yield (device->host); job inputs uploaded once at setup',
+               'd2h_bytes_per_step': int(H * W * 3 * 4), 'timed': 'wall clock around K optimizer steps of '
+               'NeuralStyleTransfer.process() incl. the per-step image yield (device->host into page-locked memory, '
+               'overlapped with the next step; rank 0 copies under sharding); job inputs uploaded once at setup',
                'setup_h2d_bytes': int(sum(a.nbytes for a in content_levels + style_levels) + init.nbytes),
                'setup_plus_first_step_s': round(first_yield_s[0], 3) if first_yield_s[0] else None}
 
@@ -426,54 +471,177 @@ def run_ours(args):
         o['calls_per_closure'] = round(o['calls_per_closure'], 1)
         o['ms_per_closure'] = round(o['ms_per_closure'], 3)
     line = {
-        'metric': METRIC, 'value': round(value, 4), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'metric': metric_name(args.levels), 'value': round(value, 4), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': round(ms / max(closures, 1), 3), 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'tf32' if (args.precision or ops.DEFAULT_PRECISION) == 'tf32' else 'f32',
         'data': 'synthetic',
-        'config': {'workload': f'L={args.levels - 1} {args.levels}-level pyramid {H}x{W}, random-init VGG19 seed 1234, '
-                               f'{args.optimizer}, structured-noise init (BASELINE configs[3])',
-                   'levels': args.levels, 'image': [H, W], 'optimizer': args.optimizer,
-                   'parallelism': f'rowband{world}' if world > 1 else 'single',
-                   'bands': parallel.PLAN.describe() if parallel.PLAN is not None else None,
-                   'cache': f'working set {mem_gb:.1f} GB per step >> {L2_BYTES / 1e6:.0f} MB L2 (no flush needed)',
-                   'closures_timed': closures, 'cuda_graph': graphed, 'cudnn_autotune': not args.no_cudnn_autotune, 'gram_operands': args.precision or ops.DEFAULT_PRECISION,
-                   'vgg_convs': 'cuDNN via torch ops on channels_last tensors (out of scope)',
-                   'kernel_table': 'separate eager pass of 3 steps, CUDA events around every launch of this library'},
+        'config': workload_config(args),
+        'impl_config': {'parallelism': f'rowband{world}' if world > 1 else 'single',
+                        'bands': parallel.PLAN.describe() if parallel.PLAN is not None else None,
+                        'peak_memory_gb': round(mem_gb, 1),
+                        'closures_timed': closures, 'cuda_graph': graphed,
+                        'cudnn_autotune': feature_path.CUDNN_BENCHMARK, 'gram_operands': args.precision or ops.DEFAULT_PRECISION,
+                        'halo': os.environ.get('AST_HALO', parallel.DEFAULT_HALO) if world > 1 else None,
+                        'vgg_convs': 'cuDNN via torch ops on channels_last tensors (out of scope)',
+                        'kernel_table': 'separate eager pass of 3 steps, CUDA events around every launch of this library'},
         'clocks': clk, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,
         'kernels': table[:20], 'own_kernels_ms_per_step': round(ours_ms / max(probe_closures, 1), 3),
         'other_bracketed_ms_per_step': other,
-        'init_image_s': round(init_s, 4), 'loss_after': loss_now,
+        'setup_kernels': kernel_table(setup_kernels, pk)[:8],
+        'init_image_s': round(init_s, 4), 'loss_after': loss_now, 'parity': parity,
     }
+    if world == 1 and not args.no_library_baseline:
+        line['library_baseline'] = library_baseline(args, dev, content_levels, style_levels, init)
+        phase('library baseline (reference torch path on this GPU) done')
     if world == 1 and not args.no_cpu_baseline:
-        line['cpu_baseline'] = cpu_baseline(steps=2, warmup=1, levels=args.levels)
+        line['cpu_baseline'] = cpu_baseline(args)
         phase('cpu baseline done')
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def first_closure_parity(job, rank, dev):
+    """Loss and image gradient of the FIRST closure (the init image: identical whatever the rank count), evaluated
+    eagerly on every rank (collective under sharding) and summarised so that runs at different N can be compared:
+    total loss, gradient L2 norm and its projection on a fixed pseudo-random direction."""
+    import torch
+    job.optimizer.zero_grad()
+    total = job._evaluate()
+    g = job.optimizing_img.grad
+    gen = torch.Generator(device=dev).manual_seed(2024)
+    direction = torch.randn(g.shape, generator=gen, device=dev)
+    out = {'loss_first': float(total.item()), 'grad_first_l2': float(g.double().norm().item()),
+           'grad_first_proj': float((g.double() * direction.double()).sum().item() / direction.double().norm().item())}
+    job.optimizing_img.grad = None
+    return out if rank == 0 else None
+
+
+# ---- the library bar: the reference's torch path on THIS GPU (BASELINE.md B3 / B4 / B6) ----------------------------
+def library_baseline(args, dev, content_levels, style_levels, init):
+    """What a user of the reference gets on the same B200 by setting device='cuda': the oracle's restatement of the
+    reference closure (torch modules + autograd, neural_style_transfer.py:152-202 without the dead CPU randn, anomaly
+    mode and prints — i.e. the reference's BEST case) under torch Adam, plus gram_matrix + MSELoss and the
+    F.interpolate chain alone.  CUDA events; these are baselines, not the product path."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import gatys_oracle as O
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, iters=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    # B3: gram_matrix + MSELoss forward + backward alone, the five tap shapes of the top level
+    top = 4 ** (args.levels - 1)
+    gram = {}
+    for c, base in ((64, 98304), (128, 24576), (256, 6144), (512, 1536), (512, 384)):
+        hw = base * top
+        g = torch.Generator(device=dev).manual_seed(c + hw)
+        x = (torch.relu(torch.randn((1, c, 1, hw), generator=g, device=dev)) * 0.25).requires_grad_(True)
+        a = torch.rand((c, c), device=dev) * 1e-3
+
+        def fwdbwd():
+            x.grad = None
+            f = x.view(1, c, hw)
+            gm = f.bmm(f.transpose(1, 2))
+            gm = gm / (c * hw)
+            F.mse_loss(a, gm[0]).backward()
+        ms = timeit(fwdbwd, iters=3)
+        gram[f'{c}x{hw}'] = {'fwdbwd_ms': round(ms, 4), 'TFLOPs': round(4.0 * c * c * hw / ms / 1e9, 1)}
+        del x
+    out['gram_mse_fwdbwd_torch_fp32'] = gram
+    # B4: the bicubic chain (levels-1 transitions) forward + backward
+    H, W = init.shape[0], init.shape[1]
+    img = torch.randn((1, 3, H, W), device=dev, requires_grad=True)
+
+    def chain():
+        img.grad = None
+        t, acc = img, 0.0
+        for _ in range(args.levels - 1):
+            t = F.interpolate(t, size=(t.shape[2] // 2, t.shape[3] // 2), mode='bicubic')
+            acc = acc + t.sum()
+        if args.levels > 1:
+            acc.backward()
+    if args.levels > 1:
+        ms = timeit(chain, iters=5)
+        byt = sum(2 * 15.0 * (H >> i) * (W >> i) for i in range(args.levels - 1))
+        out['interpolate_chain_fwdbwd'] = {'ms': round(ms, 4), 'GBps': round(byt / ms / 1e6, 1)}
+    del img
+    # B6: the closure + Adam, end to end on the device
+    net, cidx, sidx = O.make_vgg19(1234)
+    net = net.to(dev)
+    targets = [O.torch_targets(net, cidx, sidx, torch.from_numpy(O.prepare_img(c)).to(dev),
+                               torch.from_numpy(O.prepare_img(s_)).to(dev)) for c, s_ in zip(content_levels, style_levels)]
+    x = torch.from_numpy(O.prepare_img(init)).to(dev).requires_grad_(True)
+    opt = torch.optim.Adam((x,), lr=10.0)
+
+    def step():
+        for g in opt.param_groups:
+            g['lr'] *= 0.999
+        opt.zero_grad()
+        _, _, grad = O.torch_closure(net, cidx, sidx, targets, x, WEIGHTS)
+        x.grad = grad
+        opt.step()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    n = 10
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / n
+    out['closure_adam'] = {'value': round(1e3 / ms, 3), 'unit': UNIT, 'ms_per_step': round(ms, 3), 'steps': n,
+                           'what': 'oracle port of the reference closure (torch modules + autograd, NCHW, cuDNN TF32 '
+                                   'convs as torch defaults, fp32 bmm) + torch Adam, device=cuda, CUDA events'}
+    del net, targets, x, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---- CPU baseline: the oracle's restatement of the reference closure on the host cores ------------------------
-def cpu_closure_setup(sample_levels):
+def cpu_closure_setup(levels):
+    """The stated job on the host: same synthetic images, same pyramid (the oracle's cv2-equivalent resize), same
+    structured-noise init (np.random.seed(0)), random-init VGG19 seed 1234, torch Adam lr 10 x 0.999 per closure."""
     import numpy as np
     import torch
     from oracle import gatys_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     content_src, style_src = synthetic_sources()
     net, cidx, sidx = O.make_vgg19(1234)
-    c_lv = [O.resize_to_level(content_src, lv) for lv in reversed(range(sample_levels))]
-    s_lv = [O.resize_to_level(style_src, lv) for lv in reversed(range(sample_levels))]
+    c_lv = [O.resize_to_level(content_src, lv) for lv in reversed(range(levels))]
+    s_lv = [O.resize_to_level(style_src, lv) for lv in reversed(range(levels))]
     targets = [O.torch_targets(net, cidx, sidx, torch.from_numpy(O.prepare_img(c)), torch.from_numpy(O.prepare_img(s)))
                for c, s in zip(c_lv, s_lv)]
-    img = torch.from_numpy(O.prepare_img(c_lv[0])).requires_grad_(True)
+    np.random.seed(0)
+    method, nf, nl, central, peripheral, dispersion = INIT_ARGS
+    init = O.structured_noise_init(c_lv[0], s_lv[0], init_method=method, noise_factor=nf, noise_levels=nl,
+                                   central=central, peripheral=peripheral, dispersion=dispersion)
+    img = torch.from_numpy(O.prepare_img(init)).requires_grad_(True)
     opt = torch.optim.Adam((img,), lr=10.0)
 
     def step():
         for g in opt.param_groups:
             g['lr'] *= 0.999
         opt.zero_grad()
-        _, _, grad = O.torch_closure(net, cidx, sidx, targets, img, WEIGHTS)
+        total, _, grad = O.torch_closure(net, cidx, sidx, targets, img, WEIGHTS)
         img.grad = grad
         opt.step()
+        return float(total)
     return step
 
 
@@ -483,49 +651,67 @@ def pixel_ratio(levels_full, levels_sample):
     return full / samp
 
 
-def cpu_baseline(steps, warmup, levels, sample_levels=2):
-    sample_levels = min(sample_levels, levels)
-    step = cpu_closure_setup(sample_levels)
-    for _ in range(warmup):
-        step()
+def cpu_baseline(args):
+    """Bounded sample for the default run: ONE real closure + Adam update of the stated job (all `levels` levels, the
+    real image sizes) after one untimed warm-up step — ~10-20 s on a GPU box's host."""
+    step = cpu_closure_setup(args.levels)      # builds the targets: 2 x levels VGG forwards warm the conv path up
     t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
-    ratio = pixel_ratio(levels, sample_levels)
-    return {'value': round(1.0 / (dt * ratio), 5), 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
-            'sample': f'{steps} closures of the {sample_levels}-level pyramid (top {256 * 2 ** (sample_levels - 1)}x'
-                      f'{384 * 2 ** (sample_levels - 1)}) at {dt:.3f} s each on {os.cpu_count()} threads, scaled to the '
-                      f'{levels}-level job by the pixel ratio {ratio:.2f} (VGG conv cost is linear in pixels)',
+    step()
+    dt = time.perf_counter() - t0
+    return {'value': round(1.0 / dt, 5), 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+            'sample': f'1 real step (1 closure of the stated {args.levels}-level job, top level {256 * 2 ** (args.levels - 1)}x'
+                      f'{384 * 2 ** (args.levels - 1)}, + Adam), {dt:.2f} s on {os.cpu_count()} threads; oracle port of the '
+                      'reference closure (no dead randn, anomaly mode or prints); `--impl reference` times K such steps',
             'sample_s_per_step': round(dt, 4)}
 
 
 def run_reference(args):
     """The reference's own algorithm for this path (oracle port: torch-CPU closure restating
     neural_style_transfer.py:84-112, :152-193 + the Adam update) on the host cores; /root/reference itself does
-    not exist on the GPU box.  Each step is a bounded sample (2-level pyramid), scaled by pixel count."""
+    not exist on the GPU box.  Every step is a REAL step of the stated job (all levels, full image sizes) when
+    warmup + steps of it fit --cpu-budget-s (they do on a GPU box: ~8 s per step at L=3); only otherwise the steps
+    are a bounded sample (fewer levels, scaled by pixel count) and the line says so."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sample_levels = min(2, args.levels)
-    step = cpu_closure_setup(sample_levels)
-    for _ in range(args.warmup):
+    t_setup = time.perf_counter()
+    step = cpu_closure_setup(args.levels)
+    t0 = time.perf_counter()
+    step()                                     # first warm-up step doubles as the probe of a real step's duration
+    probe = time.perf_counter() - t0
+    real = probe * (args.warmup + args.steps) <= args.cpu_budget_s or args.levels == 1
+    sample_levels, ratio = args.levels, 1.0
+    if not real:
+        sample_levels = args.levels
+        while sample_levels > 1 and probe / pixel_ratio(args.levels, sample_levels) * (args.warmup + args.steps) > args.cpu_budget_s:
+            sample_levels -= 1
+        ratio = pixel_ratio(args.levels, sample_levels)
+        del step
+        step = cpu_closure_setup(sample_levels)
+        step()
+    for _ in range(max(args.warmup - 1, 0)):
         step()
     t0 = time.perf_counter()
+    loss = None
     for _ in range(args.steps):
-        step()
+        loss = step()
     dt = (time.perf_counter() - t0) / args.steps
-    ratio = pixel_ratio(args.levels, sample_levels)
     value = 1.0 / (dt * ratio)
-    sample = (f'{args.steps} closures of the {sample_levels}-level pyramid at {dt:.3f} s each on {os.cpu_count()} '
-              f'threads, scaled to the {args.levels}-level job by the pixel ratio {ratio:.2f}')
-    line = {'impl': 'reference', 'metric': METRIC, 'value': round(value, 5), 'unit': UNIT,
+    if real:
+        sample = (f'{args.steps} real steps of the stated {args.levels}-level job at {dt:.3f} s each on {os.cpu_count()} '
+                  'threads (no sampling, no scaling)')
+    else:
+        sample = (f'{args.steps} closures of the {sample_levels}-level pyramid at {dt:.3f} s each on {os.cpu_count()} '
+                  f'threads, scaled to the {args.levels}-level job by the pixel ratio {ratio:.2f} (a real step took '
+                  f'{probe:.1f} s: {args.warmup + args.steps} of them exceed the {args.cpu_budget_s:.0f} s budget)')
+    line = {'impl': 'reference', 'metric': metric_name(args.levels), 'value': round(value, 5), 'unit': UNIT,
             'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': round(dt * ratio * 1e3, 1), 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'L={args.levels - 1} {args.levels}-level pyramid 2048x3072, random-init VGG19 seed 1234, '
-                                   'adam (CPU, oracle port of the reference closure)', 'levels': args.levels,
-                       'optimizer': 'adam'},
+            'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args),
+            'impl_config': {'what': 'CPU, oracle port of the reference closure (torch modules + autograd) + torch Adam',
+                            'sampled': not real, 'sample_levels': sample_levels, 'threads': os.cpu_count(),
+                            'setup_s': round(t0 - t_setup, 1)},
+            'loss_after': loss,
             'cpu_baseline': {'value': round(value, 5), 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
                              'sample': sample},
             'e2e': {'value': round(value, 5), 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}

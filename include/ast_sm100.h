@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 3
+#define AST_ABI_VERSION 4
 
 #define AST_OK               0
 #define AST_ERR_INVALID     -1   /* bad argument (null pointer, non-positive size, misalignment) */
@@ -130,6 +130,12 @@ int ast_maxpool2x2_bwd_nhwc(const float* gy, const float* x, int C, int H, int W
 int ast_chw_to_hwc(const float* x, int C, int64_t HW, int64_t plane_stride, float* y, void* stream);
 int ast_hwc_to_chw(const float* x, int C, int64_t HW, float* y, int64_t plane_stride, int accumulate,
                    void* stream);
+/* unprepare_img (neural_style_transfer.py:388-393), the device half of the per-step image yield (:207-208):
+ * planar (3, HW) image in "x*255 - mean" units -> interleaved (HW, 3) in [0,1], y = fl32(fl32(x + mean_c) / 255)
+ * with the mean added in double exactly as numpy's in-place float32 += float64 does.  HW % 4 == 0.  The result is
+ * a snapshot: the optimizer may overwrite x as soon as this kernel has run, while the snapshot travels to the host. */
+int ast_unprepare_hwc(const float* x_chw, int64_t HW, double mean0, double mean1, double mean2,
+                      float* y_hwc, void* stream);
 
 /* ---- Halo rows of a row-band sharded level through NVLink peer memory (EXPERIMENTAL, off by default) ------
  * The reference has no multi-GPU path (a commented-out device round-robin, neural_style_transfer.py:238-243);

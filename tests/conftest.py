@@ -45,3 +45,15 @@ def seeded_vgg(monkeypatch):
 
     monkeypatch.setattr(neural_nets.models, 'vgg19', seeded)
     return seeded
+
+
+@pytest.fixture(autouse=True)
+def cudnn_heuristics_for_parity():
+    """Parity tests compare two evaluations of the same convolutions (sharded vs unsharded, graph vs eager, product vs
+    oracle): keep cuDNN on its heuristics so both sides run the same engine.  The product default (engine search on,
+    feature_path.CUDNN_BENCHMARK) is exercised by test_gpu_closure.py::test_cudnn_engine_search_default."""
+    from artstyletransfer_b200 import feature_path
+    old = feature_path.CUDNN_BENCHMARK
+    feature_path.CUDNN_BENCHMARK = False
+    yield
+    feature_path.CUDNN_BENCHMARK = old

@@ -34,7 +34,9 @@ def test_header_symbols_are_exported_and_bound(lib):
 
 
 def test_version_and_sizes(lib):
-    assert lib.ast_version() == 3
+    from artstyletransfer_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'ast_sm100.h')).read()
+    assert lib.ast_version() == _lib.AST_ABI_VERSION == int(re.search(r'#define AST_ABI_VERSION (\d+)', hdr).group(1))
     assert lib.ast_reduce_workspace_bytes() >= 16384
     # workspace covers 148 split-K partials of the largest tile plus the reduce header
     assert lib.ast_gram_workspace_bytes(512, 98304) == 32768 + 148 * 256 * 256 * 4

@@ -193,3 +193,108 @@ def test_cuda_graph_closure_matches_eager(seeded_vgg, opt):
     np.testing.assert_allclose(out[True][1], out[False][1], rtol=1e-6)
     assert torch.equal(out[True][2], out[False][2])
     assert torch.equal(out[True][3], out[False][3])
+
+
+def test_cudnn_engine_search_default(seeded_vgg):
+    """The shipped default lets cuDNN time its engines per convolution shape (what bench.py measures): same loss to the
+    stated 1e-4 and same gradient to the TF32 budget as the heuristic engines."""
+    from artstyletransfer_b200 import feature_path, neural_style_transfer as nst
+    import importlib, os
+    assert os.environ.get('AST_CUDNN_BENCHMARK', '1') == '0' or \
+        'CUDNN_BENCHMARK = os.environ.get(\'AST_CUDNN_BENCHMARK\', \'1\') != \'0\'' in open(feature_path.__file__).read()
+    torch.backends.cudnn.allow_tf32 = True            # the product's real convolution arithmetic
+    content, style = O.synthetic_images(128, 192, seed=6)
+    init = np.clip(content * 0.6 + np.random.default_rng(7).uniform(0, 1, size=content.shape) * 0.4, 0, 1).astype(np.float32)
+    out = {}
+    for search in (False, True):
+        feature_path.CUDNN_BENCHMARK = search
+        job = nst._Job(dev(), 'vgg19', [style], 'adam', [content], init, 1.0, *WEIGHTS, 'autotune')
+        job.optimizer.zero_grad()
+        total = job._evaluate()
+        out[search] = (float(total), job.optimizing_img.grad.clone())
+    assert abs(out[True][0] - out[False][0]) <= 1e-3 * abs(out[False][0])     # TF32 convolutions, different engines
+    gerr = float(torch.linalg.norm(out[True][1] - out[False][1]) / torch.linalg.norm(out[False][1]))
+    assert gerr < 2e-2, gerr
+
+
+def test_unprepare_kernel_matches_reference_arithmetic():
+    """ast_unprepare_hwc == the reference's unprepare_img (neural_style_transfer.py:388-393) bit for bit: numpy adds the
+    float64 mean to the float32 array in place (double sum, rounded to float), then divides by 255 in float32."""
+    from artstyletransfer_b200 import neural_style_transfer as nst, ops
+    g = torch.Generator(device='cuda').manual_seed(9)
+    for h, w in ((64, 96), (50, 6), (256, 384)):
+        x = (torch.rand((1, 3, h, w), generator=g, device=dev()) * 300 - 130).contiguous()
+        y = torch.empty((h, w, 3), device=dev())
+        ops.unprepare_hwc(x, y, nst.IMAGENET_MEAN_255)
+        ref = x.cpu().numpy().transpose(0, 2, 3, 1)[0].copy()
+        ref += np.array(nst.IMAGENET_MEAN_255).reshape((1, 1, 3))
+        ref = ref.astype(np.float32) / 255
+        assert np.array_equal(y.cpu().numpy(), ref)
+        assert np.array_equal(nst.unprepare_img(x), ref)
+        assert np.array_equal(O.unprepare_img(x.cpu().numpy()), ref)
+
+
+@pytest.mark.parametrize('opt', ['adam', 'lbfgs'])
+def test_async_yield_is_the_reference_sequence(seeded_vgg, opt):
+    """process() with the overlapped yield (snapshot kernel + side-stream copy + look-ahead step) yields exactly the
+    (image, step) sequence of the blocking loop, including when the consumer stops early."""
+    from artstyletransfer_b200 import neural_style_transfer as nst
+    content, style = O.synthetic_images(64, 96, seed=2)
+    init = np.clip(content * 0.6 + np.random.default_rng(5).uniform(0, 1, size=content.shape) * 0.4, 0, 1).astype(np.float32)
+
+    async def run(n_take):
+        drv = nst.NeuralStyleTransfer(dev(), 'vgg19', [style], opt)
+        res = []
+        async for img, step in drv.process([content], init, 1.0, 8, *WEIGHTS, 'yield-test'):
+            res.append((np.array(img, copy=True), step))
+            if len(res) == n_take:
+                break
+        return res
+
+    out = {}
+    try:
+        for mode in (False, True):
+            nst.ASYNC_YIELD = mode
+            out[mode] = asyncio.run(run(100))
+        early = asyncio.run(run(2))
+    finally:
+        nst.ASYNC_YIELD = True
+    assert [s for _, s in out[True]] == [s for _, s in out[False]]
+    assert len(out[True]) == (8 if opt == 'adam' else 4)
+    for (a, _), (b, _) in zip(out[True], out[False]):
+        assert np.array_equal(a, b)
+    assert len(early) == 2 and np.array_equal(early[1][0], out[True][1][0])
+
+
+def test_two_concurrent_jobs_like_the_reference_executor(seeded_vgg):
+    """task_executor.py:9 runs simultaneous_tasks_count = 2 jobs in one process: two process() generators interleaved
+    on one event loop (closures on executor threads, both capturing CUDA graphs) must each reproduce their solo run."""
+    from artstyletransfer_b200 import neural_style_transfer as nst
+    jobs = []
+    for seed in (2, 3):
+        content, style = O.synthetic_images(64, 96, seed=seed)
+        init = np.clip(content * 0.6 + np.random.default_rng(seed).uniform(0, 1, size=content.shape) * 0.4, 0, 1).astype(np.float32)
+        jobs.append((content, style, init))
+
+    async def one(content, style, init, out):
+        drv = nst.NeuralStyleTransfer(dev(), 'vgg19', [style], 'adam')
+        async for img, step in drv.process([content], init, 1.0, 8, *WEIGHTS, 'concurrent'):
+            out.append((np.array(img, copy=True), step))
+            await asyncio.sleep(0)
+
+    async def both(outs):
+        await asyncio.gather(*[one(*j, o) for j, o in zip(jobs, outs)])
+
+    solo = [[], []]
+    for j, o in zip(jobs, solo):
+        asyncio.run(one(*j, o))
+    together = [[], []]
+    strict, nst.GRAPH_STRICT = nst.GRAPH_STRICT, True        # a capture broken by the other job must fail the test
+    try:
+        asyncio.run(both(together))
+    finally:
+        nst.GRAPH_STRICT = strict
+    for s, t in zip(solo, together):
+        assert [k for _, k in s] == [k for _, k in t] == list(range(1, 9))
+        for (a, _), (b, _) in zip(s, t):
+            assert np.array_equal(a, b)

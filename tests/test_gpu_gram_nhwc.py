@@ -64,6 +64,34 @@ def test_gram_fwd_nhwc_matches_nchw_kernel(c, hw):
     assert rel(g1.cpu().numpy(), g2.cpu().numpy()) < 1e-6
 
 
+@pytest.mark.parametrize('hw', [24576, 98304])
+def test_gram_fwd_c512_both_layouts_at_vgg_sizes_repeated(hw):
+    """relu4_1 of the 1024x1536 / 2048x3072 levels (C = 512), what every LossBuilder.__init__ sends through
+    math_utils.gram_matrix: NCHW and (HW, C) operands, 25 back-to-back launches each with the L2 flushed in between
+    (the round-1 tuning sweep once died with a launch failure at the NCHW shape under a non-default pipeline shape)."""
+    from artstyletransfer_b200 import ops
+    c = 512
+    f = _feat(c, hw, 11)
+    fn = f.t().contiguous()
+    ws = ops.gram_workspace(c, hw, dev())
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev())
+    g_nhwc = torch.empty((c, c), device=dev()); g_nchw = torch.empty((c, c), device=dev())
+    first = None
+    for it in range(25):
+        flush.zero_()
+        ops.gram_mse_fwd_nhwc(f, c, hw, 1.0 / (c * hw), None, g_nhwc, None, ws)
+        ops.gram_mse_fwd(fn, c, hw, 1.0 / (c * hw), None, g_nchw, None, ws, 0)
+        if it % 8 == 0:
+            torch.cuda.synchronize()
+            if first is None:
+                first = (g_nhwc.clone(), g_nchw.clone())
+            assert torch.equal(g_nhwc, first[0]) and torch.equal(g_nchw, first[1])
+    torch.cuda.synchronize()
+    assert rel(g_nhwc.cpu().numpy(), g_nchw.cpu().numpy()) < 1e-6
+    trace_ref = (f.double() ** 2).sum().item() / (c * hw)
+    assert abs(g_nhwc.double().trace().item() - trace_ref) / trace_ref < 1e-4
+
+
 @pytest.mark.parametrize('c,hw', SHAPES)
 @pytest.mark.parametrize('accumulate', [False, True])
 def test_gram_bwd_nhwc_vs_oracle(c, hw, accumulate):
