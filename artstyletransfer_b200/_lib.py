@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libast_sm100.so')
 
-AST_ABI_VERSION = 4
+AST_ABI_VERSION = 5
 AST_PREC_TF32, AST_PREC_FP32 = 0, 1
 AST_LAYOUT_CHW, AST_LAYOUT_HWC = 0, 1
 AST_COORD_TORCH, AST_COORD_CV2 = 0, 1
@@ -36,7 +36,14 @@ class HaloRow(C.Structure):
                 ('bytes', C.c_int64), ('slot_stride', C.c_int64)]
 
 
+class FinalizeItem(C.Structure):
+    """struct ast_finalize_item (include/ast_sm100.h)."""
+    _fields_ = [('G_raw', C.c_void_p), ('A', C.c_void_p), ('out', C.c_void_p), ('loss', C.c_void_p),
+                ('scale', C.c_float), ('C', C.c_int32), ('round_out', C.c_int32), ('pad_', C.c_int32)]
+
+
 AST_HALO_MAX_ROWS = 16
+AST_FINALIZE_MAX_ITEMS = 32
 _p, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 
 # name -> (restype, argtypes); one entry per declaration in include/ast_sm100.h
@@ -49,6 +56,8 @@ SIGNATURES = {
     'ast_gram_mse_fwd': (_i, [_p, _i, _i64, _i64, _f, _p, _p, _p, _p, _sz, _i, _p]),
     'ast_gram_finalize': (_i, [_p, _i, _f, _p, _p, _p, _p, _sz, _i, _p]),
     'ast_gram_bwd': (_i, [_p, _p, _i, _i64, _i64, _f, _p, _p, _i, _i, _p]),
+    'ast_finalize_batch_workspace_bytes': (_sz, [_i]),
+    'ast_gram_finalize_batch': (_i, [C.POINTER(FinalizeItem), _i, _p, _sz, _p]),
     'ast_gram_mse_fwd_nhwc': (_i, [_p, _i, _i64, _f, _p, _p, _p, _p, _sz, _i, _p]),
     'ast_gram_bwd_nhwc': (_i, [_p, _p, _i, _i64, _f, _p, _p, _i, _i, _i, _p]),
     'ast_reduce_workspace_bytes': (_sz, []),

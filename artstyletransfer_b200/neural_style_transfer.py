@@ -15,6 +15,7 @@ with VERBOSE = True), the deepcopy before the per-step device->host copy (:207).
 from __future__ import annotations
 
 import asyncio
+import concurrent.futures
 import os
 import threading
 import traceback
@@ -65,9 +66,13 @@ ASYNC_YIELD = os.environ.get('AST_ASYNC_YIELD', '1') != '0'
 YIELD_ON_ALL_RANKS = os.environ.get('AST_YIELD_ALL_RANKS', '0') == '1'
 
 # The reference runs up to simultaneous_tasks_count = 2 jobs in one process (config.py:1, task_executor.py:9): their
-# closures come from different executor threads and their set-up / yields from the event-loop thread.  A CUDA-graph
-# capture must not overlap another thread's cudaMalloc / cudaHostAlloc, so captures use thread-local capture mode AND
-# are serialised against the allocation-heavy helpers (job set-up, init image, resize, the yield's pinned block).
+# closures come from different executor threads, all on the device's default (legacy) stream.  While one job captures
+# its closure into a CUDA graph NO other thread may touch the device: an allocation breaks a global-mode capture, and
+# any launch on the legacy stream is an implicit dependency on the capturing streams (cudaErrorStreamCaptureImplicit,
+# measured on a B200: it invalidates the capture and poisons the autograd engine thread the two jobs share).  So
+# every host-side GPU section of a job — set-up, init image, resize, one optimizer step (closure + update), the
+# yield's snapshot — holds this process-wide lock.  The GPU executes the two jobs' kernels back to back on one stream
+# anyway; the lock only serialises their host-side enqueueing.
 _GPU_SETUP_LOCK = threading.RLock()
 
 
@@ -325,7 +330,8 @@ class _Job:
             raise
 
     def optimizer_step(self):
-        return self.optimizer.step(self.closure)
+        with _GPU_SETUP_LOCK:
+            return self.optimizer.step(self.closure)
 
 
 class NeuralStyleTransfer:
@@ -341,25 +347,48 @@ class NeuralStyleTransfer:
         job = _Job(self.__device, self.__model_name, self.__style_imgs, self.__optimizer_name, content_imgs, init_img,
                    lr_start, content_weight, style_weight, tv_weight, init_img_name)
         loop = asyncio.get_running_loop()
+        # The reference hands optimizer.step to the loop's default executor (:206).  Here every step of a job runs on
+        # ONE worker thread of its own: cuDNN handles (and their device workspaces) are per thread in torch, and a
+        # step that landed on a fresh pool thread inside the CUDA-graph capture would make cuDNN allocate there
+        # (CUDNN_STATUS_INTERNAL_ERROR_DEVICE_ALLOCATION_FAILED, seen on a B200 once the pool had grown).
+        worker = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix='ast-job')
+        steps = self.__steps(job, loop, worker, iters_num)
+        try:
+            async for item in steps:
+                yield item
+        finally:
+            await steps.aclose()             # lets a look-ahead step in flight finish before its thread goes away
+            worker.shutdown(wait=False)
+
+    @staticmethod
+    async def __steps(job, loop, worker, iters_num):
         if not ASYNC_YIELD:
-            # the main optimization loop (:205-208): optimizer.step runs on the default executor's worker thread
+            # the main optimization loop (:205-208)
             while job.step < iters_num:
-                await loop.run_in_executor(None, job.optimizer_step)
-                yield unprepare_img(job.optimizing_img), job.step
+                await loop.run_in_executor(worker, job.optimizer_step)
+                with _GPU_SETUP_LOCK:
+                    img = unprepare_img(job.optimizing_img)
+                yield img, job.step
             return
         # Same loop, same (image, step) sequence, with the yield overlapped: after step k has been enqueued its image
         # is snapshotted on the device (in stream order, before step k+1 can touch it), step k+1 is handed to the
         # executor, and only then is the snapshot's device->host copy awaited and yielded.
         yielder = _ImageYielder(job.optimizing_img)
-        pending = loop.run_in_executor(None, job.optimizer_step) if job.step < iters_num else None
+
+        def step_and_snapshot():
+            """Executor thread: one optimizer step, then the snapshot of its image — enqueued back to back under the
+            GPU lock, so the next step (this job's or another job's) cannot slip in between."""
+            with _GPU_SETUP_LOCK:
+                job.optimizer_step()
+                return yielder.begin(), job.step
+
+        pending = loop.run_in_executor(worker, step_and_snapshot) if job.step < iters_num else None
         try:
             while pending is not None:
                 fut, pending = pending, None
-                await fut
-                step = job.step
-                ticket = yielder.begin()
+                ticket, step = await fut
                 if step < iters_num:
-                    pending = loop.run_in_executor(None, job.optimizer_step)
+                    pending = loop.run_in_executor(worker, step_and_snapshot)    # step k+1 runs while image k travels
                 img = await loop.run_in_executor(None, yielder.finish, ticket)
                 yield img, step
         finally:
@@ -372,7 +401,7 @@ class NeuralStyleTransfer:
 
 class _ImageYielder:
     """The per-step image yield of process() (:207-208: deepcopy, unprepare_img, device->host) off the critical path.
-    begin() — called between two optimizer steps — enqueues ONE kernel on the current stream that writes the
+    begin() — called right after an optimizer step, under the GPU lock — enqueues ONE kernel on the current stream that writes the
     unprepared (H, W, 3) [0,1] image into one of two device staging buffers (that is the snapshot: the next step may
     overwrite the leaf as soon as it has run), and the device->host copy into a fresh page-locked block on a side
     stream.  finish() waits for that copy only.  Under row-band sharding every rank holds the same image; rank 0

@@ -67,7 +67,7 @@ class KernelStats:
 STATS = KernelStats()
 
 # kernels launched per C-ABI entry point
-_KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_mse_fwd_nhwc': 2, 'ast_gram_bwd_nhwc': 1, 'ast_gram_finalize': 1, 'ast_gram_bwd': 1, 'ast_mse_fwd': 1, 'ast_mse_bwd': 1,
+_KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_mse_fwd_nhwc': 2, 'ast_gram_bwd_nhwc': 1, 'ast_gram_finalize': 1, 'ast_gram_finalize_batch': 1, 'ast_gram_bwd': 1, 'ast_mse_fwd': 1, 'ast_mse_bwd': 1,
                      'ast_tv_fwd': 1, 'ast_tv_bwd': 1, 'ast_level_combine': 1, 'ast_bicubic_down2x': 1,
                      'ast_bicubic_down2x_adj': 1, 'ast_bicubic_resize': 1, 'ast_bicubic_resize_adj': 1,
                      'ast_noise_init': 1, 'ast_bias_relu_nhwc': 1, 'ast_relu_bwd': 1, 'ast_maxpool2x2_nhwc': 1,
@@ -196,6 +196,24 @@ def gram_finalize(g_raw: torch.Tensor, C: int, scale: float, target: Optional[to
     _launch(g_raw.device, ('gram_finalize', C), 'ast_gram_finalize', g_raw.data_ptr(), C, scale,
             target.data_ptr() if target is not None else None, out.data_ptr(),
             loss.data_ptr() if loss is not None else None, ws.ptr, ws.nbytes, int(round_out))
+
+
+def gram_finalize_batch(items, ws: Workspace) -> None:
+    """items: sequence of (g_raw, C, scale, target or None, out, loss or None, round_out) — ast_gram_finalize for all of
+    them in one launch; ws from finalize_batch_workspace(len(items), device)."""
+    if len(items) > L.AST_FINALIZE_MAX_ITEMS:
+        raise ValueError(f'at most {L.AST_FINALIZE_MAX_ITEMS} Grams per batched finalize; got {len(items)}')
+    arr = (L.FinalizeItem * len(items))()
+    for i, (g_raw, c, scale, target, out, loss, round_out) in enumerate(items):
+        arr[i].G_raw, arr[i].A = g_raw.data_ptr(), (target.data_ptr() if target is not None else None)
+        arr[i].out, arr[i].loss = out.data_ptr(), (loss.data_ptr() if loss is not None else None)
+        arr[i].scale, arr[i].C, arr[i].round_out = float(scale), int(c), int(bool(round_out))
+    _launch(items[0][0].device, ('gram_finalize_batch', len(items)), 'ast_gram_finalize_batch', arr, len(items), ws.ptr,
+            ws.nbytes)
+
+
+def finalize_batch_workspace(n_items: int, device: torch.device) -> Workspace:
+    return Workspace(L.load().ast_finalize_batch_workspace_bytes(n_items), device)
 
 
 def gram_bwd(D: torch.Tensor, feat: torch.Tensor, C: int, HW: int, scale: float, gscale: Optional[torch.Tensor],

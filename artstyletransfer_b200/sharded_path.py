@@ -309,35 +309,49 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
             c, hw_band = f.shape[1], f.shape[2] * f.shape[3]
             ops.gram_mse_fwd_nhwc(f, c, hw_band, 1.0, None, packed[sh.offs[j]:sh.offs[j] + c * c], None,
                                   sh.wss.for_gram(j, c, hw_band, dev))
-        ops.mse_fwd(taps[li][sh.cidx], sh.target_content_band, 1.0, packed[sh.content_slot],
+        # partial content MSE already carries 1/numel of the WHOLE map: the all-reduced slot is the level's content loss
+        ops.mse_fwd(taps[li][sh.cidx], sh.target_content_band, 1.0 / sh.content_numel_global, packed[sh.content_slot],
                     sh.wss.for_reduce('content', dev))
 
     lanes.each(active, partials)
     with ops.timed(dev, ('allreduce_packed_grams', n_packed)):
         grp.all_reduce_sum(packed_all)
-    out4s, per_level = [], []
+    # every rank finalises identically: ALL Grams of ALL levels in one launch (D = G/(C HW) - A rounded to TF32 for the
+    # backward's operand, per-layer MSE), then per level TV + the weighted sum
+    items, ds_all, vals_all = [], [], []
     for li, sh in enumerate(levels):
-        packed, im = packs[li], imgs[li]
-        cw, sw, tvw = sh.weights
+        packed = packs[li]
         n_style = len(sh.sidx)
-        vals = torch.empty(n_style + 2, dtype=torch.float32, device=dev)
-        out4 = torch.empty(4, dtype=torch.float32, device=dev)
+        vals = torch.empty(n_style + 1, dtype=torch.float32, device=dev)   # style mse[n] | tv
         ds = {}
         for j, k in enumerate(sh.sidx):
             c = sh.channels[j]
             st_ = par.LAYER_STRIDE[k]
             hw_global = (sh.H // st_) * (sh.W // st_)
             d = torch.empty((c, c), dtype=torch.float32, device=dev)
-            ops.gram_finalize(packed[sh.offs[j]:sh.offs[j] + c * c], c, 1.0 / (c * hw_global), sh.target_grams[j], d,
-                              vals[j], sh.fin_ws[j], round_out=True)
+            items.append((packed[sh.offs[j]:sh.offs[j] + c * c], c, 1.0 / (c * hw_global), sh.target_grams[j], d, vals[j],
+                          True))
             ds[k] = (d, hw_global)
-        torch.mul(packed[sh.content_slot], 1.0 / sh.content_numel_global, out=vals[n_style])
+        ds_all.append(ds)
+        vals_all.append(vals)
+    sh0 = levels[0]
+    fin_ws = getattr(sh0, 'fin_batch_ws', None)
+    if fin_ws is None or fin_ws[0] < len(items):
+        fin_ws = sh0.fin_batch_ws = (len(items), ops.finalize_batch_workspace(len(items), dev))
+    for a in range(0, len(items), ops.L.AST_FINALIZE_MAX_ITEMS):
+        ops.gram_finalize_batch(items[a:a + ops.L.AST_FINALIZE_MAX_ITEMS], fin_ws[1])
+    out4s, per_level = [], []
+    for li, sh in enumerate(levels):
+        packed, im, vals = packs[li], imgs[li], vals_all[li]
+        cw, sw, tvw = sh.weights
+        n_style = len(sh.sidx)
+        out4 = torch.empty(4, dtype=torch.float32, device=dev)
         sums2 = torch.empty(2, dtype=torch.float32, device=dev)
-        ops.tv_fwd(im, sums2, vals[n_style + 1], sh.wss.for_reduce('tv', dev))
-        ops._launch(dev, ('combine',), 'ast_level_combine', vals.data_ptr(), n_style, vals[n_style].data_ptr(),
-                    vals[n_style + 1].data_ptr(), cw, sw, tvw, out4.data_ptr())
+        ops.tv_fwd(im, sums2, vals[n_style], sh.wss.for_reduce('tv', dev))
+        ops._launch(dev, ('combine',), 'ast_level_combine', vals.data_ptr(), n_style, packed[sh.content_slot].data_ptr(),
+                    vals[n_style].data_ptr(), cw, sw, tvw, out4.data_ptr())
         out4s.append(out4)
-        per_level.append((sh, sh.generation, ds, im, sums2))
+        per_level.append((sh, sh.generation, ds_all[li], im, sums2))
     return out4s, per_level
 
 

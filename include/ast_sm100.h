@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 4
+#define AST_ABI_VERSION 5
 
 #define AST_OK               0
 #define AST_ERR_INVALID     -1   /* bad argument (null pointer, non-positive size, misalignment) */
@@ -78,6 +78,25 @@ int ast_gram_mse_fwd(const float* F, int C, int64_t HW, int64_t ld, float scale,
  * when `out` = D only feeds ast_gram_bwd_nhwc(..., d_prerounded = 1): the backward's converter warps then skip D. */
 int ast_gram_finalize(const float* G_raw, int C, float scale, const float* A, float* out,
                       float* loss, void* ws, size_t ws_bytes, int round_out, void* stream);
+
+/* The same finalize for up to AST_FINALIZE_MAX_ITEMS raw Grams in ONE launch (row-band sharding: the all-reduced
+ * packed buffer of every pyramid level holds five of them; 20 launches per L=3 closure become one).  Every item is
+ * out = scale * G_raw - (A ? A : 0), *loss = mean(out^2) (loss may be NULL), out rounded to TF32 when round_out.
+ * ws: ast_finalize_batch_workspace_bytes(n_items) bytes, zero-filled once, reusable. */
+#define AST_FINALIZE_MAX_ITEMS 32
+typedef struct ast_finalize_item {
+  const float* G_raw;
+  const float* A;        /* nullable */
+  float*       out;
+  float*       loss;     /* nullable */
+  float        scale;
+  int32_t      C;
+  int32_t      round_out;
+  int32_t      pad_;
+} ast_finalize_item;
+size_t ast_finalize_batch_workspace_bytes(int n_items);
+int ast_gram_finalize_batch(const ast_finalize_item* items, int n_items, void* ws, size_t ws_bytes,
+                            void* stream);
 
 /* Backward of the style term (autograd of bmm + MSELoss in the reference, 2 bmm per layer):
  *   dF[C,HW] (+)= scale * D D-symmetric [C,C] * F[C,HW]

@@ -195,3 +195,28 @@ def test_mse_bwd_fused_relu_backward():
         ops.mse_bwd(x, t, 0.25, None, b, acc, False)
         b = torch.where(x > 0, b, torch.zeros_like(b))
         assert torch.equal(a, b)
+
+
+def test_gram_finalize_batch_matches_single_finalize():
+    """ast_gram_finalize_batch (all Grams of all pyramid levels in one launch, sharded path) == ast_gram_finalize item
+    by item: same D bits (incl. TF32 rounding of the stored D), losses equal to fp32 round-off, reusable workspace."""
+    from artstyletransfer_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(21)
+    items, singles = [], []
+    for n, c in enumerate([64, 128, 256, 512, 512, 64, 128]):
+        raw = torch.rand((c, c), generator=g, device=dev()) * 1e4
+        a = torch.rand((c, c), generator=g, device=dev()) * 1e-2 if n != 5 else None
+        scale = 1.0 / (c * 1000.0 * (n + 1))
+        rnd = n % 2 == 0
+        d_b = torch.empty((c, c), device=dev()); l_b = torch.empty((), device=dev()) if n != 6 else None
+        d_s = torch.empty((c, c), device=dev()); l_s = torch.empty((), device=dev())
+        items.append((raw, c, scale, a, d_b, l_b, rnd))
+        ops.gram_finalize(raw, c, scale, a, d_s, l_s, ops.reduce_workspace(dev()), round_out=rnd)
+        singles.append((d_s, l_s))
+    ws = ops.finalize_batch_workspace(len(items), dev())
+    for _ in range(2):                                   # second launch: the workspace must have been left reusable
+        ops.gram_finalize_batch(items, ws)
+        for (raw, c, scale, a, d_b, l_b, rnd), (d_s, l_s) in zip(items, singles):
+            assert torch.equal(d_b, d_s)
+            if l_b is not None:
+                assert abs(float(l_b) - float(l_s)) <= 1e-6 * abs(float(l_s))

@@ -85,6 +85,52 @@ def product_adam(dev, lr, precision=None, steps=50, seed=1):
         neural_nets.models.vgg19 = real
 
 
+def product_grad_error_along_trajectory(dev, lr, precision='tf32', autotune=False, steps=50, seed=1):
+    """Relative error of the product's image gradient against the oracle's float64 gradient AT THE PRODUCT'S OWN
+    iterates (steps 0, 10, 25, 49): how big is the per-step perturbation the chaotic trajectory amplifies?"""
+    import torchvision
+    from artstyletransfer_b200 import feature_path, neural_nets, neural_style_transfer as nst
+    real = torchvision.models.vgg19
+    neural_nets.models.vgg19 = lambda pretrained=False, progress=False, **kw: (torch.manual_seed(1234), real(weights=None))[1]
+    content, style = O.synthetic_images(64, 96, seed=seed)
+    c_lv = [content, O.bicubic_resize_hwc(content, 48, 32).astype(np.float32)]
+    s_lv = [style, O.bicubic_resize_hwc(style, 48, 32).astype(np.float32)]
+    init = np.clip(content * 0.6 + np.random.default_rng(4).uniform(0, 1, size=content.shape) * 0.4, 0, 1).astype(np.float32)
+    nst.PRECISION = precision
+    old_bm, feature_path.CUDNN_BENCHMARK = feature_path.CUDNN_BENCHMARK, autotune
+    try:
+        job = nst._Job(dev, 'vgg19', s_lv, 'adam', c_lv, init, lr, *WEIGHTS, 'graderr')
+        net, cidx, sidx = O.make_vgg19(1234)
+        net64 = net.to(dev).double()
+        t64 = [O.torch_targets(net64, cidx, sidx, torch.from_numpy(O.prepare_img(c)).to(dev).double(),
+                               torch.from_numpy(O.prepare_img(s)).to(dev).double()) for c, s in zip(c_lv, s_lv)]
+        net32, _, _ = O.make_vgg19(1234)
+        net32 = net32.to(dev)
+        t32 = [O.torch_targets(net32, cidx, sidx, torch.from_numpy(O.prepare_img(c)).to(dev),
+                               torch.from_numpy(O.prepare_img(s)).to(dev)) for c, s in zip(c_lv, s_lv)]
+        out = {}
+        for k in range(steps):
+            if k in (0, 10, 25, 49):
+                x = job.optimizing_img.detach().clone()
+                l64, _, g64 = O.torch_closure(net64, cidx, sidx, t64, x.double(), WEIGHTS)
+                l32, _, g32 = O.torch_closure(net32, cidx, sidx, t32, x, WEIGHTS)
+                job.optimizer.zero_grad()
+                lp = job._evaluate()
+                gp = job.optimizing_img.grad.double()
+                out[k] = {'product_grad_err': float((gp - g64).norm() / g64.norm()),
+                          'oracle_fp32_grad_err': float((g32.double() - g64).norm() / g64.norm()),
+                          'product_loss_err': abs(float(lp) - float(l64)) / float(l64),
+                          'oracle_fp32_loss_err': abs(float(l32) - float(l64)) / float(l64), 'loss': float(l64)}
+                job.optimizing_img.grad = None
+            job.optimizer_step()
+        final = O.unprepare_img(job.optimizing_img.detach().cpu().numpy())
+        return out, final
+    finally:
+        nst.PRECISION = None
+        feature_path.CUDNN_BENCHMARK = old_bm
+        neural_nets.models.vgg19 = real
+
+
 if __name__ == '__main__':
     dev = torch.device('cuda', 0) if '--device' in sys.argv and 'cuda' in sys.argv else torch.device('cpu')
     if dev.type == 'cuda':
@@ -94,6 +140,15 @@ if __name__ == '__main__':
     for lr in (10.0, 1.0):
         base, f = floors(dev, lr)
         if dev.type == 'cuda' and '--product' in sys.argv:
-            for prec in ('tf32', 'fp32'):
-                f[f'product_{prec}_dB'] = round(O.psnr(product_adam(dev, lr, prec), base), 2)
+            from artstyletransfer_b200 import feature_path
+            for autotune in (False, True):
+                feature_path.CUDNN_BENCHMARK = autotune
+                for prec in ('tf32', 'fp32'):
+                    f[f'product_{prec}_{"search" if autotune else "heur"}_dB'] = round(O.psnr(product_adam(dev, lr, prec), base), 2)
+            feature_path.CUDNN_BENCHMARK = False
+        if dev.type == 'cuda' and '--graderr' in sys.argv:
+            for autotune in (False, True):
+                traj, final = product_grad_error_along_trajectory(dev, lr, 'tf32', autotune)
+                f[f'tf32_{"search" if autotune else "heur"}_trajectory'] = traj
+                f[f'tf32_{"search" if autotune else "heur"}_direct_dB'] = round(O.psnr(final, base), 2)
         print(json.dumps({'device': str(dev), 'lr_start': lr, 'steps': 50, **f}), flush=True)
