@@ -272,70 +272,102 @@ def row_error_profile(diff, ref):
 
 LOCKSTEP_CASES = [(2, 'uniform', 2), (4, 'uniform', 2), (2, 'pyramid', 3), (3, 'pyramid', 3), (4, 'pyramid', 3),
                   (8, 'pyramid', 3)]
-# TF32 Gram operands: the same image-gradient budget as the unsharded closure (tests/test_gpu_closure.py)
-GRAD_BUDGET_TF32 = 2e-3
+
+
+@pytest.fixture()
+def correctly_rounded_convs(monkeypatch):
+    """Replace the four cuDNN call sites of the feature path by float64 convolutions rounded once to float32.
+
+    Why: cuDNN's fp32 result for one output pixel depends (at the 1e-7 level) on the problem shape — a row band and
+    the whole level take different tilings — and VGG19's max-pools / ReLUs are discontinuous: a 1-ulp difference
+    flips the arg-max of a near-tied 2x2 window (~1e6 windows per closure, ~1 flip expected) and re-routes that
+    window's gradient.  Measured on a B200 (tests/tools/shard_error_probe.py, profiles/r02_shard_error_probe.log): the
+    sharded-vs-unsharded gradient differs by 1e-7 everywhere EXCEPT around one or two pixels per closure, far from
+    any band edge and at the SAME pixel whatever the band layout — that is what made the 5e-4 bound of round 1 fail
+    on one box and pass on another.  With correctly rounded convolutions both paths see bit-identical activations,
+    no window can flip, and everything that IS this repo's code (bands, halo exchange, lock-step schedule, pooling
+    and ReLU glue, partial Grams + all-reduce + finalize, bicubic chain) can be held to fp32 summation order."""
+    from artstyletransfer_b200 import feature_path as fp, sharded_path as sp
+    CL = torch.channels_last
+
+    def fwd(x, w, b):
+        y = torch.nn.functional.conv2d(x.double().contiguous(), w.double().contiguous(), b.double(), padding=1)
+        return y.relu_().float().contiguous(memory_format=CL)
+
+    def dgrad(g, x, w):
+        gi = torch.nn.grad.conv2d_input(x.shape, w.double().contiguous(), g.double().contiguous(), stride=1, padding=1)
+        return gi.float().contiguous(memory_format=CL)
+
+    monkeypatch.setattr(fp, '_conv_relu_fwd', fwd)
+    monkeypatch.setattr(fp, '_conv_bwd_data', dgrad)
+    monkeypatch.setattr(sp, '_conv_relu_fwd_padded', fwd)
+    monkeypatch.setattr(sp, '_conv_bwd_data_padded', dgrad)
+
+
+def summarise(tag, run, world):
+    gsum = sum(run['grads'])
+    gerr = float(torch.linalg.norm(gsum - run['ref_grad']) / torch.linalg.norm(run['ref_grad']))
+    prof = row_error_profile(gsum - run['ref_grad'], run['ref_grad'])
+    lerr = max(abs(t - run['ref_total']) / abs(run['ref_total']) for t in run['totals'])
+    print(f'{tag} plan {run["plan"].describe()}: loss rel err {lerr:.2e}, gradient sharded-vs-unsharded {gerr:.3e}, '
+          f'row error median {np.median(prof):.2e} max {prof.max():.2e} at row {int(prof.argmax())}')
+    for r in range(world):
+        assert run['totals'][r] == run['totals'][0]                     # every rank sees bit-identical losses
+    return lerr, gerr
 
 
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize('world,bands,n_levels', LOCKSTEP_CASES)
-def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, world, bands, n_levels):
+def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, correctly_rounded_convs, world, bands, n_levels):
     """The pyramid levels evaluated in lock-step with grouped halo exchanges == the unsharded closure (bicubic chain
     + every level + backward), summed over the emulated ranks.  'uniform': every level cut into `world` equal bands;
     'pyramid': the level-aware plan (parallel.PyramidBands) — unequal bands, ranks that own rows of two levels, ranks
     that own nothing of a level and are skipped by their neighbours' exchange.
 
-    Tolerance.  Nothing in the band scheme is approximate (test_lockstep_pyramid_is_exact_without_gram_noise below
-    shows 1e-5 agreement once the TF32 Gram is out of the loss), but the two paths round DIFFERENT values: the Gram
-    is a sum over positions, its split-K order differs between one 148-CTA launch and per-band launches + all-reduce,
-    D = G - A is ~1e-2 of G (cancellation), and D is then rounded to TF32 (2^-11) as the backward's operand — a
-    1-ulp fp32 difference in G flips TF32 roundings of D.  So sharded-vs-unsharded is bounded by the TF32 noise of
-    EACH against the true (float64) gradient, not by a number tuned on one box:
-      * both paths are within the TF32 gradient budget (2e-3) of the float64 oracle gradient;
-      * the sharded path is no further from it than the unsharded one (x1.5 + 1e-4 slack);
-      * the difference is not concentrated at band edges (a halo bug would be): rows within 2 of a band edge of the
-        top level carry no more error than 3x the typical row."""
-    from artstyletransfer_b200.parallel import PyramidBands  # noqa: F401
+    Convolutions are correctly rounded (see the fixture), so the only legitimate differences are this library's own
+    summation orders: the Gram is a sum over positions whose split-K order differs between one 148-CTA launch and
+    per-band launches + all-reduce (1e-7 of G), D = G - A amplifies that by |G|/|D| ~ 1e2 and is then rounded to TF32
+    for the backward's operand — a bounded, band-edge-free 1e-5-level effect.  Asserted: loss 1e-5, gradient 1e-4."""
     run = run_lockstep(world, bands, n_levels)
-    pb, ref_total, ref_grad = run['plan'], run['ref_total'], run['ref_grad']
+    pb = run['plan']
     if bands == 'pyramid' and world > 2:           # the plan really is heterogeneous at these sizes
         assert any(pb.band(li, r)[0] == pb.band(li, r)[1] for li in range(n_levels) for r in range(world))
-    for r in range(world):
-        assert abs(run['totals'][r] - ref_total) <= 1e-4 * abs(ref_total)
-        assert run['totals'][r] == run['totals'][0]
-    gsum = sum(run['grads'])
-    g64 = fp64_closure_grad(run, WEIGHTS)
-    n64 = torch.linalg.norm(g64)
-    e_un = float(torch.linalg.norm(ref_grad.double() - g64) / n64)
-    e_sh = float(torch.linalg.norm(gsum.double() - g64) / n64)
-    gerr = float(torch.linalg.norm(gsum - ref_grad) / torch.linalg.norm(ref_grad))
-    prof = row_error_profile(gsum - ref_grad, ref_grad)
-    edges = sorted({e for e in pb.bounds[0][1:-1] if 0 < e < run['sizes'][0][0]})
-    near = sorted({r for e in edges for r in range(e - 2, e + 2)})
-    typical = float(np.median(prof))
-    worst_edge = float(prof[near].max()) if near else 0.0
-    print(f'lockstep[{world}-{bands}-{n_levels}] sharded-vs-unsharded={gerr:.3e} unsharded-vs-fp64={e_un:.3e} '
-          f'sharded-vs-fp64={e_sh:.3e} row error: median={typical:.3e} max={prof.max():.3e} at band edges {edges}: '
-          f'{worst_edge:.3e}')
-    assert e_un < GRAD_BUDGET_TF32 and e_sh < GRAD_BUDGET_TF32, (e_un, e_sh)
-    assert e_sh <= 1.5 * e_un + 1e-4, (e_sh, e_un)
-    assert gerr <= e_un + e_sh + 1e-6, (gerr, e_un, e_sh)           # triangle inequality: a sanity check of the probe
-    assert worst_edge <= 3.0 * typical + 1e-6, (worst_edge, typical, edges)
+    lerr, gerr = summarise(f'lockstep[{world}-{bands}-{n_levels}]', run, world)
+    assert lerr <= 1e-5, lerr
+    assert gerr <= 1e-4, gerr
 
 
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize('world,bands,n_levels', [(2, 'pyramid', 3), (4, 'pyramid', 3), (4, 'uniform', 2)])
-def test_lockstep_pyramid_is_exact_without_gram_noise(seeded_vgg, world, bands, n_levels):
+def test_lockstep_pyramid_is_exact_without_gram_noise(seeded_vgg, correctly_rounded_convs, world, bands, n_levels):
     """Style weight 0 and the content term moved to the deepest tap (relu5_1): the gradient then flows through every
-    convolution, pool, halo exchange and the bicubic chain but through no TF32 Gram, so the sharded closure must
-    reproduce the unsharded one to fp32 summation order (convolutions are fp32-exact in this module)."""
+    convolution, pool, halo exchange and the bicubic chain but through no TF32 Gram, so with correctly rounded
+    convolutions the sharded closure must reproduce the unsharded one to fp32 summation order."""
     weights = (1e3, 0.0, 1e2)
     run = run_lockstep(world, bands, n_levels, weights=weights, content_idx=5)
-    for r in range(world):
-        assert abs(run['totals'][r] - run['ref_total']) <= 2e-6 * abs(run['ref_total'])
-    gsum = sum(run['grads'])
-    gerr = float(torch.linalg.norm(gsum - run['ref_grad']) / torch.linalg.norm(run['ref_grad']))
-    print(f'exact[{world}-{bands}-{n_levels}] sharded-vs-unsharded={gerr:.3e}')
-    assert gerr < 5e-5, gerr
+    lerr, gerr = summarise(f'exact[{world}-{bands}-{n_levels}]', run, world)
+    assert lerr <= 2e-6, lerr
+    assert gerr < 2e-5, gerr
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('world,bands,n_levels', [(2, 'pyramid', 3), (8, 'pyramid', 3)])
+def test_lockstep_pyramid_with_cudnn_convs_is_within_pool_flip_noise(seeded_vgg, world, bands, n_levels):
+    """The same comparison with the REAL (cuDNN fp32) convolutions.  Band and whole-level shapes round differently, a
+    handful of near-tied max-pool windows flip, and each flip re-routes one window's gradient: the difference is a
+    few isolated patches (the float64 oracle shows the same patches against EITHER path), not an edge effect.  Bound:
+    loss 1e-4 (BASELINE), gradient 5e-3 overall — a broken halo row would be a 1e-1 effect along a whole band edge —
+    and both paths inside the TF32 gradient budget (2e-3, tests/test_gpu_closure.py) of the float64 gradient unless a
+    flip separates them from it too."""
+    run = run_lockstep(world, bands, n_levels)
+    lerr, gerr = summarise(f'cudnn[{world}-{bands}-{n_levels}]', run, world)
+    g64 = fp64_closure_grad(run, WEIGHTS)
+    n64 = torch.linalg.norm(g64)
+    e_un = float(torch.linalg.norm(run['ref_grad'].double() - g64) / n64)
+    e_sh = float(torch.linalg.norm(sum(run['grads']).double() - g64) / n64)
+    print(f'   vs float64 oracle: unsharded {e_un:.3e}, sharded {e_sh:.3e}')
+    assert lerr <= 1e-4, lerr
+    assert gerr < 5e-3 and e_sh < 5e-3 and e_un < 5e-3, (gerr, e_sh, e_un)
 
 
 def test_band_plan_and_pack_layout():
