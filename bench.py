@@ -58,6 +58,9 @@ def parse():
                     help='leave cuDNN on its heuristics (default: time its engines once per convolution shape)')
     ap.add_argument('--profile', default=None, help='write a torch.profiler kernel table of 3 timed-mode steps (rank 0) to this path')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ncu-closure', action='store_true',
+                    help='for `ncu --profile-from-start off`: set the job up, run 2 eager closures, then ONE eager closure + '
+                         'optimizer update between cudaProfilerStart/Stop, and exit (no timing, no JSON line)')
     ap.add_argument('--no-library-baseline', action='store_true',
                     help='skip the torch/cuDNN/cuBLAS "library bar" (the reference closure with device=cuda) at N=1')
     ap.add_argument('--cpu-budget-s', type=float, default=480.0,
@@ -332,6 +335,17 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     phase('job set up (targets, band plan)')
+    if args.ncu_closure:
+        nst.GRAPH_CLOSURE = False
+        for _ in range(2):
+            job.optimizer_step()
+        barrier()
+        torch.cuda.profiler.start()
+        job.optimizer_step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        phase('one eager closure profiled')
+        return
     # ---- device-resident timing ------------------------------------------------------------------------
     clocks = ClockSampler(local_rank)
     if rank == 0:
