@@ -150,9 +150,12 @@ struct FwdParams {
   float* partials;
 };
 
-// NU = K units per pipeline stage (one mbarrier round trip per stage), G = converter groups of 128 threads; all
-// 128 * G threads round every stage together (a 64 KB stage of the C = 512 off-diagonal tile takes as long to round
-// with 128 threads as its 8 MMAs take to run).
+// NU = K units per pipeline stage (one mbarrier round trip per stage), G = converter groups of 128 threads.  The
+// groups take ALTERNATE stages (group g rounds stages g, g + G, ...): rounding a stage is a latency chain — wait for the
+// TMA, one shared-memory round trip, membar, proxy fence, arrive; ncu (profiles/r02_ncu_gram_stalls.md) shows one group
+// finishing a 16 KB stage every ~700 cycles while HBM delivers one every ~600 — and two groups working on different
+// stages overlap their chains.  (Round 1 split every stage over all 128 * G threads instead, which shortens the
+// copy but not the chain: < 1 % gain.)
 template <int C, int NU, int G>
 struct FwdCfg {
   static constexpr int kBoxRows = (C == 64) ? 64 : (C == 128 ? 128 : 256);
@@ -166,10 +169,14 @@ struct FwdCfg {
   static constexpr int kTmemCols = (C <= 128) ? 128 : 512;
   static constexpr int kTR = (C <= 256) ? C : 256;                     // partial tile edge
   static constexpr int kUmmaN = (C <= 128) ? 128 : 256;
+  // C = 512: the two diagonal tiles fill only half of a 64 KB stage, so their CTAs cut the same ring into twice as
+  // many 32 KB stages (6 instead of 3: the MMAs of a 32 KB stage last ~640 cycles, three stages in flight did not
+  // cover the TMA latency).  kMaxStages bounds the barrier arrays.
+  static constexpr int kMaxStages = (C == 512) ? 2 * kStages : kStages;
   static constexpr int kBarBytes = 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + kBarBytes;
   static_assert(kStages >= 2, "pipeline needs two stages");
-  static_assert((3 * kStages + 1) * 8 + 8 <= kBarBytes, "barrier area too small");
+  static_assert((3 * kMaxStages + 1) * 8 + 8 <= kBarBytes, "barrier area too small");
 };
 
 // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..2+4G: converters, then epilogue.
@@ -177,14 +184,14 @@ template <int C, int NU, int G, bool NHWC>
 __global__ void __launch_bounds__(64 + 128 * G, 1) gram_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                     const __grid_constant__ FwdParams P) {
   using Cfg = FwdCfg<C, NU, G>;
-  constexpr int S = Cfg::kStages;
+  constexpr int SM = Cfg::kMaxStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
-  // bars[0..S) full, [S..2S) conv, [2S..3S) empty, [3S] acc_full ; then tmem slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
-  const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + S), bar_empty = smem_u32(bars + 2 * S),
-                 bar_acc = smem_u32(bars + 3 * S);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  // bars[0..SM) full, [SM..2SM) conv, [2SM..3SM) empty, [3SM] acc_full ; then tmem slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * SM + 1);
+  const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + SM), bar_empty = smem_u32(bars + 2 * SM),
+                 bar_acc = smem_u32(bars + 3 * SM);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // which tile / split am I?
@@ -198,12 +205,16 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) gram_fwd_tc_kernel(const __gr
   const int n_stages = (n_units + NU - 1) / NU;
   const bool offdiag = (C == 512) && (P.tile_bi[t] != P.tile_bj[t]);
   const int unit_tx_bytes = (C == 512) ? (offdiag ? 65536 : 32768) : Cfg::kUnitBytes;
+  // ring geometry of this CTA (see kMaxStages): stage stride and count
+  const int unit_stride = (C == 512 && !offdiag) ? 32768 : Cfg::kUnitBytes;
+  const int stage_stride = NU * unit_stride;
+  const int S = (C == 512 && !offdiag) ? SM : Cfg::kStages;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap);
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < SM; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_conv + 8 * s, 128 * G);
+      mbar_init(bar_conv + 8 * s, 128);       // ONE converter group per stage
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_acc, 1);
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) gram_fwd_tc_kernel(const __gr
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
           if (j < nu) {
-            const uint32_t dst = smem_u32(smem + s * Cfg::kStageBytes + j * Cfg::kUnitBytes);
+            const uint32_t dst = smem_u32(smem + s * stage_stride + j * unit_stride);
             const int u = u_begin + i * NU + j;
             if (NHWC) {
               // (HW, C) operand: 4 KB strips of [32 positions][32 channels]; coordinates (channel in strip,
@@ -270,7 +281,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) gram_fwd_tc_kernel(const __gr
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
           if (j < nu) {
-            const uint32_t a_base = smem_u32(smem + s * Cfg::kStageBytes + j * Cfg::kUnitBytes);
+            const uint32_t a_base = smem_u32(smem + s * stage_stride + j * unit_stride);
             const uint32_t b_base = offdiag ? a_base + 256 * ROW_BYTES : a_base;
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
@@ -296,20 +307,20 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) gram_fwd_tc_kernel(const __gr
       umma_commit(bar_acc);
     }
   } else {
-    // ===== converters (G groups of 128 threads), then epilogue =====
+    // ===== converters (G groups of 128 threads taking alternate stages), then epilogue =====
     const int grp = (warp - 2) >> 2;
-    const int ctid = threadIdx.x - 64;               // 0 .. 128 * G - 1
-    for (int i = 0; i < n_stages; ++i) {
+    const int ctid = (threadIdx.x - 64) & 127;       // thread within its group
+    for (int i = grp; i < n_stages; i += G) {
       const int s = i % S;
       const uint32_t ph = (uint32_t)(i / S) & 1u;
       const int nu = min(NU, n_units - i * NU);
       mbar_wait(bar_full + 8 * s, ph);
       if (P.skip_rounding) {
-      } else if (unit_tx_bytes == Cfg::kUnitBytes) {
-        convert_tf32_inplace<128 * G>(smem + s * Cfg::kStageBytes, nu * Cfg::kUnitBytes, ctid);
+      } else if (unit_tx_bytes == unit_stride) {
+        convert_tf32_inplace<128>(smem + s * stage_stride, nu * unit_stride, ctid);
       } else {
         for (int j = 0; j < nu; ++j)
-          convert_tf32_inplace<128 * G>(smem + s * Cfg::kStageBytes + j * Cfg::kUnitBytes, unit_tx_bytes, ctid);
+          convert_tf32_inplace<128>(smem + s * stage_stride + j * unit_stride, unit_tx_bytes, ctid);
       }
       fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(bar_conv + 8 * s);
@@ -895,10 +906,16 @@ __global__ void __launch_bounds__(BwdNhwcCfg<C, W>::kThreads, 1) gram_bwd_nhwc_t
 // MMA.  A pair of CTAs (two SMs of a TPC) computes M = 256 positions per MMA: each CTA keeps its own 128 positions
 // of F and only HALF of the B operand (128 of the 256 output channels of each N block), so per CTA the D traffic
 // halves (TMA 48 KB, tensor-core reads 64 KB per chunk) and four stages fit where two did.
-// Protocol (s = stage): each CTA's TMA fills its full[s]; its converters round the F part and arrive on the
-// LEADER's conv[s] (count 256, the peer's through shared::cluster); the leader's MMA thread issues
-// tcgen05.mma.cta_group::2 and commits with a multicast arrive on empty[s] of BOTH CTAs; the accumulator-full
-// commit is multicast too; both CTAs' epilogue warps arrive on the leader's acc_empty.
+// Protocol (s = stage): each CTA's TMA fills its full[s]; its converters round the F part and arrive on their OWN
+// CTA's conv[s] (count 128, cta scope: a MEMBAR.ALL.CTA).  Round 1 had all 256 converter threads arrive on the LEADER's
+// barrier with a cluster-scope release, which ptxas turns into MEMBAR.ALL.GPU + ERRBAR per thread and stage: ncu's
+// source page (profiles/r02_ncu_gram_stalls.md) shows the converter warps stalled there (~1 400 of 8 700 samples, the
+// largest single stall of the kernel), i.e. one converter warp-group finished a stage only every ~2 500 cycles for
+// 1 300 cycles of MMA.  Now ONE otherwise idle thread of the peer CTA (lane 0 of warp 1) relays: it waits on the peer's
+// local conv[s] and does the single cluster-scope arrive on the leader's peer[s]; the leader's MMA thread waits for
+// conv[s] (its own converters) and peer[s], issues tcgen05.mma.cta_group::2 and commits with a multicast arrive on
+// empty[s] of BOTH CTAs; the accumulator-full commit is multicast too; the epilogue warps arrive on their own CTA's
+// acc_empty and the same relay thread forwards the peer's to the leader.
 struct Bwd2CtaCfg {
   static constexpr int C = 512;
   static constexpr int kFBytes = 128 * ROW_BYTES;                 // 16 KB: this CTA's 128 positions x 32 channels
@@ -908,6 +925,7 @@ struct Bwd2CtaCfg {
   static constexpr int kOutBytes = 4 * 2 * 4096;
   static constexpr int kThreads = 320;
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + 256;
+  static_assert((4 * kStages + 4) * 8 <= 256, "barrier area too small");
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
@@ -919,10 +937,11 @@ gram_bwd_nhwc_2cta_kernel(const __grid_constant__ CUtensorMap tmapF, const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ostage = smem + S * Cfg::kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + Cfg::kOutBytes);
-  // full[S] conv[S] empty[S] acc_full acc_empty
+  // full[S] conv[S] empty[S] peer[S] acc_full acc_empty acc_empty_peer
   const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + S), bar_empty = smem_u32(bars + 2 * S),
-                 bar_accf = smem_u32(bars + 3 * S), bar_acce = smem_u32(bars + 3 * S + 1);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 2);
+                 bar_peer = smem_u32(bars + 3 * S), bar_accf = smem_u32(bars + 4 * S),
+                 bar_acce = smem_u32(bars + 4 * S + 1), bar_accp = smem_u32(bars + 4 * S + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * S + 3);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -935,11 +954,13 @@ gram_bwd_nhwc_2cta_kernel(const __grid_constant__ CUtensorMap tmapF, const __gri
     prefetch_tmap(&tmapO);
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_conv + 8 * s, 256);     // both CTAs' converters (only the leader's copy is used)
+      mbar_init(bar_conv + 8 * s, 128);     // this CTA's converters
       mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_peer + 8 * s, 1);       // the peer's relay thread (only the leader's copy is used)
     }
     mbar_init(bar_accf, 1);
-    mbar_init(bar_acce, 256);               // both CTAs' epilogue warps (leader's copy)
+    mbar_init(bar_acce, 128);               // this CTA's epilogue warps
+    mbar_init(bar_accp, 1);                 // the peer's relay thread (leader's copy)
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -976,11 +997,13 @@ gram_bwd_nhwc_2cta_kernel(const __grid_constant__ CUtensorMap tmapF, const __gri
       int it = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
         mbar_wait(bar_acce, ((uint32_t)ti & 1u) ^ 1u);    // both epilogues have drained the accumulator
+        mbar_wait(bar_accp, ((uint32_t)ti & 1u) ^ 1u);
         tc_fence_after();
         for (int kc = 0; kc < KC; ++kc, ++it) {
           const int s = it % S;
           const uint32_t ph = (uint32_t)(it / S) & 1u;
-          mbar_wait(bar_conv + 8 * s, ph);
+          mbar_wait(bar_conv + 8 * s, ph);                // my converters ...
+          mbar_wait(bar_peer + 8 * s, ph);                // ... and the peer's (relayed)
           tc_fence_after();
           const uint32_t f_base = smem_u32(smem + s * Cfg::kStageBytes);
           const uint32_t d_base = f_base + Cfg::kFBytes;
@@ -995,19 +1018,34 @@ gram_bwd_nhwc_2cta_kernel(const __grid_constant__ CUtensorMap tmapF, const __gri
         }
         umma_commit_2cta(bar_accf, 3);
       }
+    } else if (lane == 0) {
+      // ===== relay (peer CTA only): forward "my converters are done with stage s" / "my epilogue has drained the
+      // accumulator" to the leader with ONE cluster-scope arrive each =====
+      const uint32_t peer0 = mapa_shared(bar_peer, 0), accp0 = mapa_shared(bar_accp, 0);
+      int it = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        if (ti > 0) {
+          mbar_wait(bar_acce, ((uint32_t)ti & 1u) ^ 1u);  // my epilogue warps have drained tile ti - 1
+          mbar_arrive_cluster(accp0);
+        }
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const int s = it % S;
+          mbar_wait(bar_conv + 8 * s, (uint32_t)(it / S) & 1u);
+          mbar_arrive_cluster(peer0 + 8 * s);
+        }
+      }
     }
   } else if (warp < 6) {
-    // ===== converters: round this CTA's F tile, then tell the leader's MMA thread =====
+    // ===== converters: round this CTA's F tile, arrive on this CTA's conv[s] (cta scope) =====
     const int ctid = threadIdx.x - 64;
     const int total = my_tiles * KC;
-    const uint32_t conv0 = mapa_shared(bar_conv, 0);
     for (int it = 0; it < total; ++it) {
       const int s = it % S;
       const uint32_t ph = (uint32_t)(it / S) & 1u;
       mbar_wait(bar_full + 8 * s, ph);
       convert_tf32_inplace(smem + s * Cfg::kStageBytes, P.d_prerounded ? Cfg::kFBytes : Cfg::kStageBytes, ctid);
       fence_proxy_async_smem();
-      mbar_arrive_cluster(conv0 + 8 * s);
+      mbar_arrive(bar_conv + 8 * s);
     }
   } else {
     // ===== epilogue (each CTA: its own 128 positions = its own TMEM lanes) =====
@@ -1017,7 +1055,6 @@ gram_bwd_nhwc_2cta_kernel(const __grid_constant__ CUtensorMap tmapF, const __gri
     const uint32_t stg = smem_u32(ostage + (warp - 6) * 8192);
     const uint32_t row_off = (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
-    const uint32_t acce0 = mapa_shared(bar_acce, 0);
     uint32_t v[32];
     uint32_t nbuf = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
@@ -1071,7 +1108,7 @@ gram_bwd_nhwc_2cta_kernel(const __grid_constant__ CUtensorMap tmapF, const __gri
         ++nbuf;
       }
       tc_fence_before();
-      mbar_arrive_cluster(acce0);
+      mbar_arrive(bar_acce);
     }
     if (lane == 0) tma_store_wait<0>();
   }
@@ -1178,11 +1215,12 @@ static void fwd_cfg(int C, int* nu, int* g) {
       env_nu = 0;
     }
   }
-  // measured on B200 (profiles/r01_fwd_cfg_sweep.log): the four shapes are within 1 % of one another, so the
-  // smallest one is the default for every C.  (Round 1 shipped G = 2 for C = 512; its sweep log holds one
-  // unexplained launch failure at exactly that shape with an NCHW operand, so G = 2 stays a tuning switch only.)
+  // Round 1 measured NU and G as neutral (profiles/r01_fwd_cfg_sweep.log) — with G groups splitting EVERY stage.
+  // Since round 2 the groups take alternate stages, which is what hides the converter's latency chain; G = 2 is the
+  // default, G = 1 the comparison.  (The one launch failure in the round-1 sweep log at NCHW C = 512 G = 2 did not
+  // reproduce in two reruns of the same sweep on a B200, profiles/r02_fwd_cfg12_rerun.log; the shape has a test.)
   *nu = env_nu ? env_nu : 1;
-  *g = env_g ? env_g : 1;
+  *g = env_g ? env_g : 2;      // two converter groups on alternate stages (round 2)
   if (C >= 256) *nu = 1;   // a stage already holds 32/64 KB
 }
 
