@@ -151,7 +151,7 @@ struct FwdParams {
 };
 
 // NU = K units per pipeline stage (one mbarrier round trip per stage), G = converter groups of 128 threads.  The
-// groups take ALTERNATE stages (group g rounds stages g, g + G, ...): rounding a stage is a latency chain — wait for the
+// groups take ALTERNATE ring slots (group g rounds slots g, g + G, ...): rounding a stage is a latency chain — wait for the
 // TMA, one shared-memory round trip, membar, proxy fence, arrive; ncu (profiles/r02_ncu_gram_stalls.md) shows one group
 // finishing a 16 KB stage every ~700 cycles while HBM delivers one every ~600 — and two groups working on different
 // stages overlap their chains.  (Round 1 split every stage over all 128 * G threads instead, which shortens the
@@ -310,8 +310,11 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) gram_fwd_tc_kernel(const __gr
     // ===== converters (G groups of 128 threads taking alternate stages), then epilogue =====
     const int grp = (warp - 2) >> 2;
     const int ctid = (threadIdx.x - 64) & 127;       // thread within its group
-    for (int i = grp; i < n_stages; i += G) {
+    for (int i = 0; i < n_stages; ++i) {
       const int s = i % S;
+      // a ring slot always belongs to the same group: a group that skipped a phase of full[s] could not tell the
+      // phase it waits for from the one before it by parity alone (S = 3 with G = 2 raced exactly like that)
+      if (G > 1 && (s % G) != grp) continue;
       const uint32_t ph = (uint32_t)(i / S) & 1u;
       const int nu = min(NU, n_units - i * NU);
       mbar_wait(bar_full + 8 * s, ph);
@@ -570,6 +573,7 @@ struct BwdNhwcParams {
   const float* F;    // (HW, C), read again by the epilogue when relu_mask is set (L2-hot: the tile was just staged)
   float* dF;
   int C;
+  int relay_release; // CTA-pair kernel: relay with release.cluster arrives (A/B switch, default relaxed)
 };
 
 // W ("wide epilogue", C = 256 only): 3 stages + 2 epilogue groups instead of 4 + 1 — the pipeline shape for the
@@ -1021,17 +1025,18 @@ gram_bwd_nhwc_2cta_kernel(const __grid_constant__ CUtensorMap tmapF, const __gri
     } else if (lane == 0) {
       // ===== relay (peer CTA only): forward "my converters are done with stage s" / "my epilogue has drained the
       // accumulator" to the leader with ONE cluster-scope arrive each =====
+      // AST_2CTA_RELAY_RELEASE=1 (P.relay_release): cluster-scope release arrives instead of relaxed ones (A/B switch)
       const uint32_t peer0 = mapa_shared(bar_peer, 0), accp0 = mapa_shared(bar_accp, 0);
       int it = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
         if (ti > 0) {
           mbar_wait(bar_acce, ((uint32_t)ti & 1u) ^ 1u);  // my epilogue warps have drained tile ti - 1
-          mbar_arrive_cluster(accp0);
+          if (P.relay_release) mbar_arrive_cluster(accp0); else mbar_arrive_cluster_relaxed(accp0);
         }
         for (int kc = 0; kc < KC; ++kc, ++it) {
           const int s = it % S;
           mbar_wait(bar_conv + 8 * s, (uint32_t)(it / S) & 1u);
-          mbar_arrive_cluster(peer0 + 8 * s);
+          if (P.relay_release) mbar_arrive_cluster(peer0 + 8 * s); else mbar_arrive_cluster_relaxed(peer0 + 8 * s);
         }
       }
     }
@@ -1304,6 +1309,7 @@ static int launch_bwd_nhwc(const float* D, const float* F, int64_t HW, float sca
   P.F = F;
   P.dF = dF;
   P.C = C;
+  P.relay_release = 0;
   cudaError_t e = cudaFuncSetAttribute(gram_bwd_nhwc_tc_kernel<C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes);
   if (e != cudaSuccess) {
@@ -1337,6 +1343,8 @@ static int launch_bwd_nhwc_2cta(const float* D, const float* F, int64_t HW, floa
   P.F = F;
   P.dF = dF;
   P.C = C;
+  static const int relay_release = (getenv("AST_2CTA_RELAY_RELEASE") && atoi(getenv("AST_2CTA_RELAY_RELEASE")) == 1) ? 1 : 0;
+  P.relay_release = relay_release;
   cudaError_t e = cudaFuncSetAttribute(gram_bwd_nhwc_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes);
   if (e != cudaSuccess) {

@@ -396,6 +396,24 @@ def run_ours(args):
     for v in summary.values():
         v['calls_per_closure'] = v['calls'] / max(probe_closures, 1)
     ops.STATS.reset(enabled=False)
+    # per-rank busy time of the eager pass (ms per closure): where a sharded step's critical path and imbalance sit
+    busy = {'cudnn': 0.0, 'own': 0.0, 'halo': 0.0, 'allreduce': 0.0}
+    for key, st in summary.items():
+        name = str(key[0])
+        per = st['ms_total'] / max(probe_closures, 1)
+        if name.startswith('cudnn'):
+            busy['cudnn'] += per
+        elif name.startswith('halo_exchange'):
+            busy['halo'] += per
+        elif name.startswith('allreduce'):
+            busy['allreduce'] += per
+        elif kernel_work(key)[0] > 0:
+            busy['own'] += per
+    busy = {k: round(v, 3) for k, v in busy.items()}
+    per_rank_busy = [busy]
+    if world > 1:
+        per_rank_busy = [None] * world
+        dist.all_gather_object(per_rank_busy, busy)
     clk = clocks.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -501,6 +519,7 @@ def run_ours(args):
         'clocks': clk, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,
         'kernels': table[:20], 'own_kernels_ms_per_step': round(ours_ms / max(probe_closures, 1), 3),
         'other_bracketed_ms_per_step': other,
+        'per_rank_busy_ms_eager_pass': per_rank_busy,
         'setup_kernels': kernel_table(setup_kernels, pk)[:8],
         'init_image_s': round(init_s, 4), 'loss_after': loss_now, 'parity': parity,
     }
