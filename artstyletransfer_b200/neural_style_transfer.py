@@ -318,7 +318,10 @@ class _Job:
             else:
                 if torch.is_grad_enabled():
                     optimizer.zero_grad()
-                total_loss = self._evaluate()
+                # detached: a caller that keeps the returned loss must not keep the autograd graph — and with it the
+                # leaf's AccumulateGrad node, created on the default stream — alive into the CUDA-graph capture, where
+                # a node of the legacy stream is an illegal dependency on the capturing stream
+                total_loss = self._evaluate().detach()
                 self._eager_closures += 1
             if VERBOSE:
                 with torch.no_grad():

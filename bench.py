@@ -53,6 +53,9 @@ def parse():
     ap.add_argument('--levels', type=int, default=LEVELS, help='pyramid levels (4 = the headline L=3 job)')
     ap.add_argument('--optimizer', default='adam', choices=['adam', 'lbfgs'])
     ap.add_argument('--precision', default=None, choices=[None, 'tf32', 'fp32'])
+    ap.add_argument('--init', default='structured', choices=['structured', 'pixel'],
+                    help="structured: Config() noise levels (9,18,36,-1,0), style-permutation noise (BASELINE configs[2],[3]); "
+                         "pixel: lab.py's PIXEL_WIDE_NOISE_CONFIG with clipped normal noise per pixel (BASELINE configs[1])")
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cudnn-autotune', action='store_true',
                     help='leave cuDNN on its heuristics (default: time its engines once per convolution shape)')
@@ -260,6 +263,12 @@ def phase(msg):
 
 INIT_ARGS = ('content+noise', 0.95, (9, 18, 36, -1, 0), (0.30, 0.20, 0.10, 0.20, 0.20), (0.20, 0.30, 0.40, 0.10, 0.00),
              (0.20, 0.30, 0.40, 0.60, 0.30))          # config.Config() defaults (config.py:10-18)
+# lab.py:26-32 PIXEL_WIDE_NOISE_CONFIG, used with USE_NORMAL_NOISE_JUST_FOR_DEMONSTRATION (neural_style_transfer.py:296-298)
+PIXEL_INIT_ARGS = ('content+noise', 0.5, (-1,), (1.0,), (1.0,), (0.5,))
+
+
+def init_args(args):
+    return PIXEL_INIT_ARGS if args.init == 'pixel' else INIT_ARGS
 
 
 def workload_config(args):
@@ -270,7 +279,9 @@ def workload_config(args):
     return {'workload': f'L={args.levels - 1} {args.levels}-level pyramid {H}x{W}, random-init VGG19 seed 1234, '
                         f'{args.optimizer}, structured-noise init (BASELINE configs[{cfg_no}])',
             'levels': args.levels, 'image': [H, W], 'optimizer': args.optimizer,
-            'weights': list(WEIGHTS), 'init': 'content+noise, Config() noise levels (9,18,36,-1,0), np.random.seed(0)',
+            'weights': list(WEIGHTS),
+            'init': ('content+noise, PIXEL_WIDE_NOISE_CONFIG, clipped normal noise per pixel, np.random.seed(0)' if args.init == 'pixel'
+                     else 'content+noise, Config() noise levels (9,18,36,-1,0), np.random.seed(0)'),
             'step': 'one optimizer.step = Adam: 1 closure (all levels fwd+bwd) + update; LBFGS: 2 closures',
             'cache': 'working set of a step (>= 1 GB of activations at every level set) >> 126 MB L2: no flush needed'}
 
@@ -288,7 +299,8 @@ def build_job(args, dev):
     pair = nst.ContentStylePair(('synthetic-content', content_src), ('synthetic-style', style_src))
     np.random.seed(0)
     t0 = time.perf_counter()
-    init, name = nst.build_init_image(pair, content_levels, style_levels, *INIT_ARGS, dev)
+    nst.USE_NORMAL_NOISE_JUST_FOR_DEMONSTRATION = args.init == 'pixel'
+    init, name = nst.build_init_image(pair, content_levels, style_levels, *init_args(args), dev)
     torch.cuda.synchronize()
     init_s = time.perf_counter() - t0
     return content_levels, style_levels, init, name, init_s
@@ -647,7 +659,7 @@ def library_baseline(args, dev, content_levels, style_levels, init):
 
 
 # ---- CPU baseline: the oracle's restatement of the reference closure on the host cores ------------------------
-def cpu_closure_setup(levels):
+def cpu_closure_setup(levels, optimizer='adam', init='structured'):
     """The stated job on the host: same synthetic images, same pyramid (the oracle's cv2-equivalent resize), same
     structured-noise init (np.random.seed(0)), random-init VGG19 seed 1234, torch Adam lr 10 x 0.999 per closure."""
     import numpy as np
@@ -661,20 +673,29 @@ def cpu_closure_setup(levels):
     targets = [O.torch_targets(net, cidx, sidx, torch.from_numpy(O.prepare_img(c)), torch.from_numpy(O.prepare_img(s)))
                for c, s in zip(c_lv, s_lv)]
     np.random.seed(0)
-    method, nf, nl, central, peripheral, dispersion = INIT_ARGS
-    init = O.structured_noise_init(c_lv[0], s_lv[0], init_method=method, noise_factor=nf, noise_levels=nl,
-                                   central=central, peripheral=peripheral, dispersion=dispersion)
-    img = torch.from_numpy(O.prepare_img(init)).requires_grad_(True)
-    opt = torch.optim.Adam((img,), lr=10.0)
+    method, nf, nl, central, peripheral, dispersion = PIXEL_INIT_ARGS if init == 'pixel' else INIT_ARGS
+    init_img = O.structured_noise_init(c_lv[0], s_lv[0], init_method=method, noise_factor=nf, noise_levels=nl,
+                                       central=central, peripheral=peripheral, dispersion=dispersion,
+                                       use_normal_noise=init == 'pixel')
+    img = torch.from_numpy(O.prepare_img(init_img)).requires_grad_(True)
+    if optimizer == 'adam':
+        opt = torch.optim.Adam((img,), lr=10.0)
+    else:   # neural_style_transfer.py:136 — one LBFGS step = 2 closures under torch >= 2.x
+        opt = torch.optim.LBFGS((img,), max_iter=1, line_search_fn='strong_wolfe', lr=10.0)
+    last = [None]
 
-    def step():
+    def closure():
         for g in opt.param_groups:
             g['lr'] *= 0.999
         opt.zero_grad()
         total, _, grad = O.torch_closure(net, cidx, sidx, targets, img, WEIGHTS)
         img.grad = grad
-        opt.step()
-        return float(total)
+        last[0] = float(total)
+        return total
+
+    def step():
+        opt.step(closure)
+        return last[0]
     return step
 
 
@@ -687,7 +708,7 @@ def pixel_ratio(levels_full, levels_sample):
 def cpu_baseline(args):
     """Bounded sample for the default run: ONE real closure + Adam update of the stated job (all `levels` levels, the
     real image sizes) after one untimed warm-up step — ~10-20 s on a GPU box's host."""
-    step = cpu_closure_setup(args.levels)      # builds the targets: 2 x levels VGG forwards warm the conv path up
+    step = cpu_closure_setup(args.levels, args.optimizer, args.init)      # builds the targets: 2 x levels VGG forwards warm the conv path up
     t0 = time.perf_counter()
     step()
     dt = time.perf_counter() - t0
@@ -708,7 +729,7 @@ def run_reference(args):
     if rank != 0:
         return
     t_setup = time.perf_counter()
-    step = cpu_closure_setup(args.levels)
+    step = cpu_closure_setup(args.levels, args.optimizer, args.init)
     t0 = time.perf_counter()
     step()                                     # first warm-up step doubles as the probe of a real step's duration
     probe = time.perf_counter() - t0
@@ -720,7 +741,7 @@ def run_reference(args):
             sample_levels -= 1
         ratio = pixel_ratio(args.levels, sample_levels)
         del step
-        step = cpu_closure_setup(sample_levels)
+        step = cpu_closure_setup(sample_levels, args.optimizer, args.init)
         step()
     for _ in range(max(args.warmup - 1, 0)):
         step()
@@ -741,7 +762,7 @@ def run_reference(args):
             'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': round(dt * ratio * 1e3, 1), 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args),
-            'impl_config': {'what': 'CPU, oracle port of the reference closure (torch modules + autograd) + torch Adam',
+            'impl_config': {'what': f'CPU, oracle port of the reference closure (torch modules + autograd) + torch {args.optimizer}',
                             'sampled': not real, 'sample_levels': sample_levels, 'threads': os.cpu_count(),
                             'setup_s': round(t0 - t_setup, 1)},
             'loss_after': loss,

@@ -61,6 +61,7 @@ def main():
         job.optimizer.zero_grad()
         total = job._evaluate()
         loss, grad = float(total.item()), job.optimizing_img.grad.clone()
+        del total                                 # drop the autograd graph (and the leaf's AccumulateGrad node) before the capture
         job.optimizing_img.grad = None
         for _ in range(args.steps):
             job.optimizer_step()
