@@ -12,14 +12,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libast_sm100.so')
 
-AST_ABI_VERSION = 5
-AST_PREC_TF32, AST_PREC_FP32 = 0, 1
+AST_ABI_VERSION = 6
+AST_PREC_TF32, AST_PREC_FP32, AST_PREC_BF16 = 0, 1, 2
 AST_LAYOUT_CHW, AST_LAYOUT_HWC = 0, 1
 AST_COORD_TORCH, AST_COORD_CV2 = 0, 1
 AST_INIT_RANDOM, AST_INIT_CONTENT_NOISE = 0, 1
 AST_NOISE_MAX_LEVELS = 16
 
-PRECISIONS = {'tf32': AST_PREC_TF32, 'fp32': AST_PREC_FP32}
+PRECISIONS = {'tf32': AST_PREC_TF32, 'fp32': AST_PREC_FP32, 'bf16': AST_PREC_BF16}
 
 
 class NoiseLevel(C.Structure):
@@ -60,6 +60,7 @@ SIGNATURES = {
     'ast_gram_finalize_batch': (_i, [C.POINTER(FinalizeItem), _i, _p, _sz, _p]),
     'ast_gram_mse_fwd_nhwc': (_i, [_p, _i, _i64, _f, _p, _p, _p, _p, _sz, _i, _p]),
     'ast_gram_bwd_nhwc': (_i, [_p, _p, _i, _i64, _f, _p, _p, _i, _i, _i, _p]),
+    'ast_gram_bwd_nhwc_bf16': (_i, [_p, _p, _i, _i64, _f, _p, _p, _i, _i, _p]),
     'ast_reduce_workspace_bytes': (_sz, []),
     'ast_mse_fwd': (_i, [_p, _p, _i64, _f, _p, _p, _sz, _p]),
     'ast_mse_bwd': (_i, [_p, _p, _i64, _f, _p, _p, _i, _i, _p]),

@@ -166,10 +166,34 @@ struct FinalizeArgs {
   int round_out;       // 1: store `out` rounded to nearest TF32 (it only feeds the backward's tensor-core operand)
 };
 
+__device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// store 4 consecutive results: fp32, fp32 rounded to TF32 (round_out 1) or bfloat16 (round_out 2; `out` then holds
+// C x C bfloat16 — the BF16 backward's D operand)
+__device__ __forceinline__ void store_d4(float* out, size_t o, const float d[4], int round_out);
+__device__ __forceinline__ void store_d1(float* out, size_t o, float d, int round_out);
+
 __device__ __forceinline__ float tf32_rn(float x) {
   // same rounding as the Gram kernels' operand converter (gram_tc.cu: half an ulp added to the magnitude)
   const uint32_t u = __float_as_uint(x);
   return ((u & 0x7f800000u) == 0x7f800000u) ? x : __uint_as_float((u + 0x1000u) & 0xffffe000u);
+}
+
+__device__ __forceinline__ void store_d4(float* out, size_t o, const float d[4], int round_out) {
+  if (round_out == 2) {
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out) + o) = make_uint2(bf16x2_rn(d[0], d[1]), bf16x2_rn(d[2], d[3]));
+  } else if (round_out == 1) {
+    *reinterpret_cast<float4*>(out + o) = make_float4(tf32_rn(d[0]), tf32_rn(d[1]), tf32_rn(d[2]), tf32_rn(d[3]));
+  } else {
+    *reinterpret_cast<float4*>(out + o) = make_float4(d[0], d[1], d[2], d[3]);
+  }
+}
+__device__ __forceinline__ void store_d1(float* out, size_t o, float d, int round_out) {
+  if (round_out == 2) reinterpret_cast<uint16_t*>(out)[o] = (uint16_t)(bf16x2_rn(d, 0.f) & 0xffffu);
+  else out[o] = round_out == 1 ? tf32_rn(d) : d;
 }
 
 __global__ void __launch_bounds__(256) gram_finalize_kernel(const __grid_constant__ FinalizeArgs a, ReduceWs* ws) {
@@ -210,16 +234,14 @@ __global__ void __launch_bounds__(256) gram_finalize_kernel(const __grid_constan
     } else {
       d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
     }
-    *reinterpret_cast<float4*>(a.out + o) = a.round_out
-                                                ? make_float4(tf32_rn(d[0]), tf32_rn(d[1]), tf32_rn(d[2]), tf32_rn(d[3]))
-                                                : make_float4(d[0], d[1], d[2], d[3]);
+    store_d4(a.out, o, d, a.round_out);
     sq = (double)d[0] * d[0] + (double)d[1] * d[1] + (double)d[2] * d[2] + (double)d[3] * d[3];
     if (a.symmetric_src && pl.tile_bi[t] != pl.tile_bj[t]) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const size_t om = (size_t)(gj + k) * C + gi;
         const float dm = a.A ? v[k] - __ldg(a.A + om) : v[k];
-        a.out[om] = a.round_out ? tf32_rn(dm) : dm;
+        store_d1(a.out, om, dm, a.round_out);
         sq += (double)dm * dm;
       }
     }
@@ -262,9 +284,7 @@ __global__ void __launch_bounds__(256) gram_finalize_batch_kernel(const __grid_c
       const float4 av = __ldg(reinterpret_cast<const float4*>(q.A) + i);
       d[0] -= av.x; d[1] -= av.y; d[2] -= av.z; d[3] -= av.w;
     }
-    reinterpret_cast<float4*>(q.out)[i] = q.round_out
-                                              ? make_float4(tf32_rn(d[0]), tf32_rn(d[1]), tf32_rn(d[2]), tf32_rn(d[3]))
-                                              : make_float4(d[0], d[1], d[2], d[3]);
+    store_d4(q.out, (size_t)i * 4, d, q.round_out);
     sq = (double)d[0] * d[0] + (double)d[1] * d[1] + (double)d[2] * d[2] + (double)d[3] * d[3];
   }
   if (!q.loss) return;
@@ -411,7 +431,7 @@ extern "C" int ast_gram_mse_fwd_nhwc(const float* F, int C, int64_t HW, float sc
   gram_tc_plan(C, HW, sms < 148 ? sms : 148, &plan);
   int rc = gram_tc_fwd(F, C, HW, C, 1, partials, plan, sms, stream);
   if (rc != AST_OK) return rc;
-  return launch_finalize(plan, partials, 1, scale, A, out, loss, ws, stream, round_out ? 1 : 0);
+  return launch_finalize(plan, partials, 1, scale, A, out, loss, ws, stream, round_out);
 }
 
 extern "C" int ast_gram_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale,
@@ -426,6 +446,18 @@ extern "C" int ast_gram_bwd_nhwc(const float* D, const float* F, int C, int64_t 
                           cached_num_sms(), stream);
 }
 
+extern "C" int ast_gram_bwd_nhwc_bf16(const void* D_bf16, const float* F, int C, int64_t HW, float scale,
+                                      const float* gscale, float* dF, int accumulate, int relu_mask, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  AST_REQUIRE(D_bf16 && F && dF, AST_ERR_INVALID, "ast_gram_bwd_nhwc_bf16: null pointer");
+  AST_REQUIRE(HW > 0 && HW <= (int64_t)0x7fffff00, AST_ERR_INVALID, "ast_gram_bwd_nhwc_bf16: bad HW=%lld", (long long)HW);
+  AST_REQUIRE(C == 512, AST_ERR_UNSUPPORTED,
+              "ast_gram_bwd_nhwc_bf16: BF16 operands are implemented for C = 512, the tensor-bound width (got %d); "
+              "narrower layers are HBM-bound and use ast_gram_bwd_nhwc", C);
+  AST_REQUIRE(is16(F) && is16(D_bf16) && is16(dF), AST_ERR_INVALID, "ast_gram_bwd_nhwc_bf16: D/F/dF must be 16-byte aligned");
+  return gram_tc_bwd_nhwc_bf16(D_bf16, F, C, HW, scale, gscale, dF, accumulate, relu_mask ? 1 : 0, cached_num_sms(), stream);
+}
+
 extern "C" int ast_gram_finalize(const float* G_raw, int C, float scale, const float* A, float* out, float* loss,
                                  void* ws, size_t ws_bytes, int round_out, void* stream) {
   AST_REQUIRE(G_raw && out && ws, AST_ERR_INVALID, "ast_gram_finalize: null pointer");
@@ -436,7 +468,7 @@ extern "C" int ast_gram_finalize(const float* G_raw, int C, float scale, const f
   plan.C = C; plan.TR = C; plan.n_tiles = 1;
   plan.tile_bi[0] = plan.tile_bj[0] = 0;
   plan.part_off[0] = 0; plan.part_cnt[0] = 1; plan.total_parts = 1;
-  return launch_finalize(plan, G_raw, 0, scale, A, out, loss, ws, (cudaStream_t)stream, round_out ? 1 : 0);
+  return launch_finalize(plan, G_raw, 0, scale, A, out, loss, ws, (cudaStream_t)stream, round_out);
 }
 
 extern "C" int ast_gram_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, float scale,

@@ -44,4 +44,8 @@ int gram_tc_bwd(const float* D, const float* F, int C, int64_t HW, int64_t ld, f
 int gram_tc_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale, float* dF,
                      int accumulate, int d_prerounded, int relu_mask, int num_sms, cudaStream_t stream);
 
+// BF16 operands (AST_PREC_BF16), C = 512 only: D is bfloat16 (C, C) as written by the finalize kernels with round_out = 2.
+int gram_tc_bwd_nhwc_bf16(const void* D_bf16, const float* F, int C, int64_t HW, float scale, const float* gscale,
+                          float* dF, int accumulate, int relu_mask, int num_sms, cudaStream_t stream);
+
 }  // namespace ast

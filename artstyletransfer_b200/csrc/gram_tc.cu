@@ -920,23 +920,63 @@ __global__ void __launch_bounds__(BwdNhwcCfg<C, W>::kThreads, 1) gram_bwd_nhwc_t
 // conv[s] (its own converters) and peer[s], issues tcgen05.mma.cta_group::2 and commits with a multicast arrive on
 // empty[s] of BOTH CTAs; the accumulator-full commit is multicast too; the epilogue warps arrive on their own CTA's
 // acc_empty and the same relay thread forwards the peer's to the leader.
+// BF16 = true (AST_PREC_BF16): operands in bfloat16, fp32 accumulation.  A K chunk is 64 channels: the F tile lands as
+// two fp32 boxes of [128 positions][32 channels]; converter thread p rounds ITS position row of both boxes to 64 bf16
+// (cvt.rn) and writes them over the first box's row p — a 128-byte bf16 row occupies exactly the 128-byte fp32 row it
+// came from, with the same 128B-swizzle key (p & 7), so the conversion is in place without any cross-thread hazard.
+// D arrives ALREADY in bf16 (ast_gram_finalize*, round_out = 2) through a bf16 tensor map: half the L2 traffic and no
+// conversion.  Per stage: 8 MMAs of K = 16 (twice the flops of the TF32 stage for the same tensor-core time).
+template <bool BF16>
 struct Bwd2CtaCfg {
   static constexpr int C = 512;
-  static constexpr int kFBytes = 128 * ROW_BYTES;                 // 16 KB: this CTA's 128 positions x 32 channels
-  static constexpr int kDHalfBytes = 128 * ROW_BYTES;             // 16 KB: 128 output channels x 32 k
-  static constexpr int kStageBytes = kFBytes + 2 * kDHalfBytes;   // 48 KB
-  static constexpr int kStages = 4;
+  static constexpr int kChunk = BF16 ? 64 : 32;                   // channels of K per stage
+  static constexpr int kFBytes = 128 * kChunk * 4;                // fp32 landing: this CTA's 128 positions
+  static constexpr int kDHalfBytes = 128 * ROW_BYTES;             // 16 KB: 128 output channels x one 128-byte K row
+  static constexpr int kStageBytes = kFBytes + 2 * kDHalfBytes;   // 48 KB (TF32) / 64 KB (BF16)
+  static constexpr int kStages = BF16 ? 3 : 4;
   static constexpr int kOutBytes = 4 * 2 * 4096;
   static constexpr int kThreads = 320;
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + 256;
   static_assert((4 * kStages + 4) * 8 <= 256, "barrier area too small");
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
+// Round one position row (64 channels) of a staged BF16 chunk in place: fp32 rows of box 0 / box 1 -> one bf16 row.
+__device__ __forceinline__ void convert_bf16_row_inplace(uint8_t* stage, int p) {
+  const uint32_t row0 = smem_u32(stage) + (uint32_t)p * 128u;     // box 0, row p (and the bf16 row)
+  const uint32_t row1 = row0 + 128u * 128u;                       // box 1, row p (16 KB further)
+  const uint32_t sw = (uint32_t)(p & 7);
+  uint32_t v[2][8][4];
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t addr = (b ? row1 : row0) + ((((uint32_t)j) ^ sw) << 4);
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(v[b][j][0]), "=r"(v[b][j][1]), "=r"(v[b][j][2]), "=r"(v[b][j][3])
+                   : "r"(addr));
+    }
+  // bf16 16-byte chunk c (channels 8c .. 8c+7) = fp32 chunks 2c, 2c+1 of box c / 4
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int b = c >> 2, j0 = (2 * c) & 7;
+    uint32_t o[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[2 * h]) : "f"(__uint_as_float(v[b][j0 + h][1])), "f"(__uint_as_float(v[b][j0 + h][0])));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[2 * h + 1]) : "f"(__uint_as_float(v[b][j0 + h][3])), "f"(__uint_as_float(v[b][j0 + h][2])));
+    }
+    const uint32_t addr = row0 + ((((uint32_t)c) ^ sw) << 4);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+  }
+}
+
+template <bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gram_bwd_nhwc_2cta_kernel(const __grid_constant__ CUtensorMap tmapF, const __grid_constant__ CUtensorMap tmapD,
                           const __grid_constant__ CUtensorMap tmapO, const __grid_constant__ BwdNhwcParams P) {
-  using Cfg = Bwd2CtaCfg;
-  constexpr int C = 512, S = Cfg::kStages, KC = C / BK;
+  using Cfg = Bwd2CtaCfg<BF16>;
+  constexpr int C = 512, S = Cfg::kStages, KC = C / Cfg::kChunk;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ostage = smem + S * Cfg::kStageBytes;
@@ -988,16 +1028,18 @@ gram_bwd_nhwc_2cta_kernel(const __grid_constant__ CUtensorMap tmapF, const __gri
           mbar_wait(bar_empty + 8 * s, ph ^ 1u);
           mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)Cfg::kStageBytes);
           const uint32_t dst = smem_u32(smem + s * Cfg::kStageBytes);
-          tma_load_2d(dst, &tmapF, bar_full + 8 * s, kc * BK, (int)n0);
-          tma_load_2d(dst + Cfg::kFBytes, &tmapD, bar_full + 8 * s, kc * BK, (int)(rank * 128));
-          tma_load_2d(dst + Cfg::kFBytes + Cfg::kDHalfBytes, &tmapD, bar_full + 8 * s, kc * BK, (int)(256 + rank * 128));
+          tma_load_2d(dst, &tmapF, bar_full + 8 * s, kc * Cfg::kChunk, (int)n0);
+          if (BF16) tma_load_2d(dst + 128 * ROW_BYTES, &tmapF, bar_full + 8 * s, kc * Cfg::kChunk + BK, (int)n0);
+          // D: fp32 rows of 32 k (TF32) or bf16 rows of 64 k (BF16) — 128 bytes either way
+          tma_load_2d(dst + Cfg::kFBytes, &tmapD, bar_full + 8 * s, kc * Cfg::kChunk, (int)(rank * 128));
+          tma_load_2d(dst + Cfg::kFBytes + Cfg::kDHalfBytes, &tmapD, bar_full + 8 * s, kc * Cfg::kChunk, (int)(256 + rank * 128));
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       // ===== MMA issuer (leader CTA only) =====
-      constexpr uint32_t idesc = umma_idesc_tf32(256, 256, 0, 0);
+      constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(256, 256, 0, 0) : umma_idesc_tf32(256, 256, 0, 0);
       int it = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
         mbar_wait(bar_acce, ((uint32_t)ti & 1u) ^ 1u);    // both epilogues have drained the accumulator
@@ -1014,9 +1056,17 @@ gram_bwd_nhwc_2cta_kernel(const __grid_constant__ CUtensorMap tmapF, const __gri
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             const uint32_t acc = (kc > 0 || k > 0) ? 1u : 0u;
+            // one K step = 32 bytes of every 128-byte row: 8 tf32 or 16 bf16
             const uint64_t ad = umma_desc_sw128(f_base + k * 32, 16, 1024);
-            umma_tf32_2cta(tmem_base, ad, umma_desc_sw128(d_base + k * 32, 16, 1024), idesc, acc);
-            umma_tf32_2cta(tmem_base + 256, ad, umma_desc_sw128(d_base + Cfg::kDHalfBytes + k * 32, 16, 1024), idesc, acc);
+            const uint64_t bd0 = umma_desc_sw128(d_base + k * 32, 16, 1024);
+            const uint64_t bd1 = umma_desc_sw128(d_base + Cfg::kDHalfBytes + k * 32, 16, 1024);
+            if (BF16) {
+              umma_bf16_2cta(tmem_base, ad, bd0, idesc, acc);
+              umma_bf16_2cta(tmem_base + 256, ad, bd1, idesc, acc);
+            } else {
+              umma_tf32_2cta(tmem_base, ad, bd0, idesc, acc);
+              umma_tf32_2cta(tmem_base + 256, ad, bd1, idesc, acc);
+            }
           }
           umma_commit_2cta(bar_empty + 8 * s, 3);
         }
@@ -1048,7 +1098,8 @@ gram_bwd_nhwc_2cta_kernel(const __grid_constant__ CUtensorMap tmapF, const __gri
       const int s = it % S;
       const uint32_t ph = (uint32_t)(it / S) & 1u;
       mbar_wait(bar_full + 8 * s, ph);
-      convert_tf32_inplace(smem + s * Cfg::kStageBytes, P.d_prerounded ? Cfg::kFBytes : Cfg::kStageBytes, ctid);
+      if (BF16) convert_bf16_row_inplace(smem + s * Cfg::kStageBytes, ctid);
+      else convert_tf32_inplace(smem + s * Cfg::kStageBytes, P.d_prerounded ? Cfg::kFBytes : Cfg::kStageBytes, ctid);
       fence_proxy_async_smem();
       mbar_arrive(bar_conv + 8 * s);
     }
@@ -1321,15 +1372,36 @@ static int launch_bwd_nhwc(const float* D, const float* F, int64_t HW, float sca
   return check_launch("gram_bwd_nhwc_tc");
 }
 
-static int launch_bwd_nhwc_2cta(const float* D, const float* F, int64_t HW, float scale, const float* gscale, float* dF,
+// D: fp32 (C, C) for TF32, bfloat16 (C, C) for BF16 (as written by ast_gram_finalize* with round_out = 2).
+template <bool BF16>
+static int launch_bwd_nhwc_2cta(const void* D, const float* F, int64_t HW, float scale, const float* gscale, float* dF,
                                 int accumulate, int d_prerounded, int relu_mask, int num_sms, cudaStream_t stream) {
-  using Cfg = Bwd2CtaCfg;
+  using Cfg = Bwd2CtaCfg<BF16>;
   constexpr int C = 512;
   CUtensorMap tmF, tmD, tmO;
   int rc = make_tmap(&tmF, F, (uint64_t)HW, C, C, 128);
   if (rc != AST_OK) return rc;
-  rc = make_tmap(&tmD, D, C, C, C, 128);
-  if (rc != AST_OK) return rc;
+  if (BF16) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+      set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+      return AST_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)C};
+    cuuint64_t gstride[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(D), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (bf16 D) failed (CUresult %d)", (int)r);
+      return AST_ERR_CUDA;
+    }
+  } else {
+    rc = make_tmap(&tmD, static_cast<const float*>(D), C, C, C, 128);
+    if (rc != AST_OK) return rc;
+  }
   rc = make_tmap(&tmO, dF, (uint64_t)HW, C, C, 32);
   if (rc != AST_OK) return rc;
   BwdNhwcParams P;
@@ -1345,7 +1417,7 @@ static int launch_bwd_nhwc_2cta(const float* D, const float* F, int64_t HW, floa
   P.C = C;
   static const int relay_release = (getenv("AST_2CTA_RELAY_RELEASE") && atoi(getenv("AST_2CTA_RELAY_RELEASE")) == 1) ? 1 : 0;
   P.relay_release = relay_release;
-  cudaError_t e = cudaFuncSetAttribute(gram_bwd_nhwc_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(gram_bwd_nhwc_2cta_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("gram_tc_bwd_nhwc(2cta): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1354,8 +1426,17 @@ static int launch_bwd_nhwc_2cta(const float* D, const float* F, int64_t HW, floa
   int pairs = num_sms / 2;
   if (pairs > P.n_tiles) pairs = P.n_tiles;
   if (pairs < 1) pairs = 1;
-  gram_bwd_nhwc_2cta_kernel<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmF, tmD, tmO, P);
+  gram_bwd_nhwc_2cta_kernel<BF16><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmF, tmD, tmO, P);
   return check_launch("gram_bwd_nhwc_2cta");
+}
+
+int gram_tc_bwd_nhwc_bf16(const void* D_bf16, const float* F, int C, int64_t HW, float scale, const float* gscale,
+                          float* dF, int accumulate, int relu_mask, int num_sms, cudaStream_t stream) {
+  if (C != 512) {
+    set_error("gram_tc_bwd_nhwc_bf16: BF16 operands are implemented for C = 512 (the tensor-bound width); got C=%d", C);
+    return AST_ERR_UNSUPPORTED;
+  }
+  return launch_bwd_nhwc_2cta<true>(D_bf16, F, HW, scale, gscale, dF, accumulate, 1, relu_mask, num_sms, stream);
 }
 
 int gram_tc_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale, const float* gscale, float* dF,
@@ -1371,7 +1452,7 @@ int gram_tc_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float sc
       // CTA-pair kernel by default; AST_GRAM_BWD_2CTA=0 selects the one-CTA kernel (comparison / fallback)
       static const int use_pair = (getenv("AST_GRAM_BWD_2CTA") && atoi(getenv("AST_GRAM_BWD_2CTA")) == 0) ? 0 : 1;
       if (use_pair)
-        return launch_bwd_nhwc_2cta(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
+        return launch_bwd_nhwc_2cta<false>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
       return launch_bwd_nhwc<512>(D, F, HW, scale, gscale, dF, accumulate, d_prerounded, relu_mask, num_sms, stream);
     }
   }

@@ -221,6 +221,26 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_ma
          | ((uint32_t)(N >> 3) << 17)       // N / 8
          | ((uint32_t)(M >> 4) << 24);      // M / 16
 }
+// Instruction descriptor for kind::f16 with bfloat16 inputs, fp32 accumulate.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4)                          // D format  : F32
+         | (1u << 7)                        // A format  : BF16
+         | (1u << 10)                       // B format  : BF16
+         | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {

@@ -255,7 +255,8 @@ class LevelPathFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, img):
-        plan, targets, content_idx, style_idx, weights, wss = cfg
+        plan, targets, content_idx, style_idx, weights, wss = cfg[:6]
+        bf16 = bool(cfg[6]) if len(cfg) > 6 else False
         dev = ops._require_cuda(img)
         cw, sw, tvw = (float(v) for v in weights)
         img = img.contiguous()
@@ -268,9 +269,9 @@ class LevelPathFn(torch.autograd.Function):
         for j, k in enumerate(style_idx):
             f = taps[k]
             c, hw = f.shape[1], f.shape[2] * f.shape[3]
-            d = torch.empty((c, c), dtype=torch.float32, device=dev)
+            d = ops.new_d(c, bf16, dev)
             ops.gram_mse_fwd_nhwc(f, c, hw, 1.0 / (c * hw), targets.grams[j], d, vals[j], wss.for_gram(j, c, hw, dev),
-                                  round_out=True)     # D only feeds the backward's tensor-core operand
+                                  round_out=ops.d_round_mode(c, bf16))     # D only feeds the backward's tensor-core operand
             ds[k] = d
         xc = taps[content_idx]
         if xc.numel() != targets.content_cl.numel():
@@ -305,8 +306,8 @@ class LevelPathFn(torch.autograd.Function):
             # the Gram kernel's fused ReLU backward pays off up to C = 256 (measured, profiles/r01_gram_nhwc_sweep.jsonl)
             fuse_gram = relu_mask and not content and c <= FUSED_TAP_RELU_MAX_C
             if style:
-                ops.gram_bwd_nhwc(ds[k], tap, c, hw, (sw / n) * 4.0 / (float(c) * c * c * hw), gsc, g, acc,
-                                  d_prerounded=True, relu_mask=fuse_gram)
+                ops.gram_bwd_nhwc_auto(ds[k], tap, c, hw, (sw / n) * 4.0 / (float(c) * c * c * hw), gsc, g, acc,
+                                       relu_mask=fuse_gram)
             if content:
                 ops.mse_bwd(tap, targets.content_cl, cw * 2.0 / tap.numel(), gsc, g, acc or style, relu_mask)
             elif not style and not acc:

@@ -40,7 +40,8 @@ SHOW_TEST_IMGS = False          # accepted for compatibility; the debug JPEG dum
 IGNORE_GRADIENT_MAP_JUST_FOR_DEMONSTRATION = False
 
 VERBOSE = False                 # True restores the reference's per-closure prints (adds host syncs)
-PRECISION = None                # None -> ops.DEFAULT_PRECISION ('tf32'); 'fp32' for the exact path
+PRECISION = None                # None -> ops.DEFAULT_PRECISION ('tf32'); 'fp32' for the exact path; 'bf16': TF32 + bfloat16
+                                # operands in the backward of the 512-channel layers (AST_PREC_BF16)
 # True: a level runs as the explicit channels-last schedule of feature_path.py (cuDNN convs without layout
 # transposes + this library's glue and (HW, C) Gram kernels).  False: torch modules + autograd around the NCHW
 # kernels (also what 'fp32' precision and non-Vgg19 feature nets use).
@@ -149,7 +150,7 @@ class LossBuilder:
 
     def __path_plan(self, optimizing_img):
         """The channels-last plan when this level can use it: TF32 Gram operands, a frozen Vgg19 on CUDA, batch 1."""
-        if not CHANNELS_LAST_PATH or ops._prec(PRECISION) != ops.L.AST_PREC_TF32:
+        if not CHANNELS_LAST_PATH or ops._prec(PRECISION) not in (ops.L.AST_PREC_TF32, ops.L.AST_PREC_BF16):
             return None
         if not (torch.is_tensor(optimizing_img) and optimizing_img.is_cuda and optimizing_img.dim() == 4
                 and optimizing_img.shape[0] == 1 and optimizing_img.dtype == torch.float32):
@@ -172,7 +173,8 @@ class LossBuilder:
                     self.__style_feature_maps_indices, self.__wss)
             cfg = (plan, self.__path_targets, self.__content_feature_maps_index,
                    tuple(self.__style_feature_maps_indices),
-                   (self.__content_weight, self.__style_weight, self.__tv_weight), self.__wss)
+                   (self.__content_weight, self.__style_weight, self.__tv_weight), self.__wss,
+                   ops._prec(PRECISION) == ops.L.AST_PREC_BF16)
             return feature_path.LevelPathFn.apply(cfg, optimizing_img)
         feats = self.__neural_net(optimizing_img)
         cfg = (self.__target_content_representation, self.__target_grams,

@@ -67,7 +67,7 @@ class KernelStats:
 STATS = KernelStats()
 
 # kernels launched per C-ABI entry point
-_KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_mse_fwd_nhwc': 2, 'ast_gram_bwd_nhwc': 1, 'ast_gram_finalize': 1, 'ast_gram_finalize_batch': 1, 'ast_gram_bwd': 1, 'ast_mse_fwd': 1, 'ast_mse_bwd': 1,
+_KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_mse_fwd_nhwc': 2, 'ast_gram_bwd_nhwc': 1, 'ast_gram_bwd_nhwc_bf16': 1, 'ast_gram_finalize': 1, 'ast_gram_finalize_batch': 1, 'ast_gram_bwd': 1, 'ast_mse_fwd': 1, 'ast_mse_bwd': 1,
                      'ast_tv_fwd': 1, 'ast_tv_bwd': 1, 'ast_level_combine': 1, 'ast_bicubic_down2x': 1,
                      'ast_bicubic_down2x_adj': 1, 'ast_bicubic_resize': 1, 'ast_bicubic_resize_adj': 1,
                      'ast_noise_init': 1, 'ast_bias_relu_nhwc': 1, 'ast_relu_bwd': 1, 'ast_maxpool2x2_nhwc': 1,
@@ -207,7 +207,7 @@ def gram_finalize_batch(items, ws: Workspace) -> None:
     for i, (g_raw, c, scale, target, out, loss, round_out) in enumerate(items):
         arr[i].G_raw, arr[i].A = g_raw.data_ptr(), (target.data_ptr() if target is not None else None)
         arr[i].out, arr[i].loss = out.data_ptr(), (loss.data_ptr() if loss is not None else None)
-        arr[i].scale, arr[i].C, arr[i].round_out = float(scale), int(c), int(bool(round_out))
+        arr[i].scale, arr[i].C, arr[i].round_out = float(scale), int(c), int(round_out)
     _launch(items[0][0].device, ('gram_finalize_batch', len(items)), 'ast_gram_finalize_batch', arr, len(items), ws.ptr,
             ws.nbytes)
 
@@ -244,6 +244,30 @@ def gram_bwd_nhwc(D: torch.Tensor, feat: torch.Tensor, C: int, HW: int, scale: f
             D.data_ptr(), feat.data_ptr() + 4 * offset, C, HW, scale,
             gscale.data_ptr() if gscale is not None else None, dF.data_ptr() + 4 * offset, int(accumulate),
             int(d_prerounded), int(relu_mask))
+
+
+BF16_MIN_C = 512      # AST_PREC_BF16: layers at least this wide take bfloat16 operands in the backward (the tensor-bound ones)
+
+
+def d_round_mode(C: int, bf16: bool) -> int:
+    """round_out of the finalize kernels for a D that only feeds the backward: 2 = bfloat16 (BF16 mode, C = 512),
+    1 = TF32-representable fp32."""
+    return 2 if (bf16 and C >= BF16_MIN_C) else 1
+
+
+def new_d(C: int, bf16: bool, device: torch.device) -> torch.Tensor:
+    return torch.empty((C, C), dtype=torch.bfloat16 if (bf16 and C >= BF16_MIN_C) else torch.float32, device=device)
+
+
+def gram_bwd_nhwc_auto(D: torch.Tensor, feat: torch.Tensor, C: int, HW: int, scale: float, gscale, dF: torch.Tensor,
+                       accumulate: bool, relu_mask: bool = False, offset: int = 0) -> None:
+    """Backward with a D produced by the finalize kernels (round_out from d_round_mode): bfloat16 D -> BF16 kernel."""
+    if D.dtype == torch.bfloat16:
+        _launch(feat.device, ('gram_bwd_nhwc_bf16', C, HW, int(accumulate) + 2 * int(relu_mask)), 'ast_gram_bwd_nhwc_bf16',
+                D.data_ptr(), feat.data_ptr() + 4 * offset, C, HW, scale, gscale.data_ptr() if gscale is not None else None,
+                dF.data_ptr() + 4 * offset, int(accumulate), int(relu_mask))
+    else:
+        gram_bwd_nhwc(D, feat, C, HW, scale, gscale, dF, accumulate, offset=offset, d_prerounded=True, relu_mask=relu_mask)
 
 
 def _gscale(g: Optional[torch.Tensor], dev: torch.device) -> Optional[torch.Tensor]:

@@ -101,6 +101,8 @@ class ShardedPathLevel:
                     group.rank + 1 if group.rank + 1 < group.world else None)
         self.r0, self.r1, self.up, self.dn = band
         self.hb = self.r1 - self.r0
+        from . import neural_style_transfer as _nst
+        self.bf16 = ops._prec(_nst.PRECISION) == ops.L.AST_PREC_BF16
         if self.hb and (self.r0 % par.ALIGN or self.r1 % par.ALIGN or not 0 <= self.r0 < self.r1 <= height):
             raise ValueError(f'band rows [{self.r0}, {self.r1}) of a {height}-row level must be multiples of {par.ALIGN}')
         dev = self.device = content_img.device
@@ -328,9 +330,9 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
             c = sh.channels[j]
             st_ = par.LAYER_STRIDE[k]
             hw_global = (sh.H // st_) * (sh.W // st_)
-            d = torch.empty((c, c), dtype=torch.float32, device=dev)
+            d = ops.new_d(c, sh.bf16, dev)
             items.append((packed[sh.offs[j]:sh.offs[j] + c * c], c, 1.0 / (c * hw_global), sh.target_grams[j], d, vals[j],
-                          True))
+                          ops.d_round_mode(c, sh.bf16)))
             ds[k] = (d, hw_global)
         ds_all.append(ds)
         vals_all.append(vals)
@@ -386,8 +388,8 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tenso
         fuse_gram = relu_mask and not content and c <= fp.FUSED_TAP_RELU_MAX_C
         if style:
             d, hw_global = ds[k]
-            ops.gram_bwd_nhwc(d, tap, c, hw_band, (sw / n) * 4.0 / (float(c) * c * c * hw_global), gsc, g, acc,
-                              d_prerounded=True, relu_mask=fuse_gram)
+            ops.gram_bwd_nhwc_auto(d, tap, c, hw_band, (sw / n) * 4.0 / (float(c) * c * c * hw_global), gsc, g, acc,
+                                   relu_mask=fuse_gram)
         if content:
             ops.mse_bwd(tap, sh.target_content_band, cw * 2.0 / sh.content_numel_global, gsc, g, acc or style,
                         relu_mask)

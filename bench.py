@@ -52,7 +52,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--levels', type=int, default=LEVELS, help='pyramid levels (4 = the headline L=3 job)')
     ap.add_argument('--optimizer', default='adam', choices=['adam', 'lbfgs'])
-    ap.add_argument('--precision', default=None, choices=[None, 'tf32', 'fp32'])
+    ap.add_argument('--precision', default=None, choices=[None, 'tf32', 'fp32', 'bf16'])
     ap.add_argument('--init', default='structured', choices=['structured', 'pixel'],
                     help="structured: Config() noise levels (9,18,36,-1,0), style-permutation noise (BASELINE configs[2],[3]); "
                          "pixel: lab.py's PIXEL_WIDE_NOISE_CONFIG with clipped normal noise per pixel (BASELINE configs[1])")
@@ -187,7 +187,7 @@ def kernel_work(key):
     if k == 'gram_fwd_nhwc':
         _, c, hw = key
         return 4.0 * c * hw + 8.0 * c * c, 2.0 * c * c * hw
-    if k == 'gram_bwd_nhwc':
+    if k in ('gram_bwd_nhwc', 'gram_bwd_nhwc_bf16'):
         _, c, hw, mode = key                 # mode bit 0: accumulate (reads dF too); bit 1: fused ReLU backward
         return (12.0 if (mode & 1) else 8.0) * c * hw + 4.0 * c * c, 2.0 * c * c * hw
     if k == 'bias_relu':
@@ -517,7 +517,8 @@ def run_ours(args):
     line = {
         'metric': metric_name(args.levels), 'value': round(value, 4), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': round(ms / max(closures, 1), 3), 'higher_is_better': True,
-        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'tf32' if (args.precision or ops.DEFAULT_PRECISION) == 'tf32' else 'f32',
+        'scaling': 'strong', 'vs_baseline': None,
+        'dtype': {'tf32': 'tf32', 'fp32': 'f32', 'bf16': 'tf32 (bf16 operands in the 512-channel backward)'}[args.precision or ops.DEFAULT_PRECISION],
         'data': 'synthetic',
         'config': workload_config(args),
         'impl_config': {'parallelism': f'rowband{world}' if world > 1 else 'single',

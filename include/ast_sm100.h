@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 5
+#define AST_ABI_VERSION 6
 
 #define AST_OK               0
 #define AST_ERR_INVALID     -1   /* bad argument (null pointer, non-positive size, misalignment) */
@@ -41,6 +41,7 @@ extern "C" {
 /* Operand precision of the Gram contractions (accumulation is always fp32). */
 #define AST_PREC_TF32 0   /* tcgen05 kind::tf32, operands rounded to nearest TF32 in shared memory */
 #define AST_PREC_FP32 1   /* exact fp32 FFMA path (what torch.bmm does with allow_tf32 = False)    */
+#define AST_PREC_BF16 2   /* TF32 everywhere except the C = 512 backward: tcgen05 kind::f16, bfloat16 operands */
 
 #define AST_LAYOUT_CHW 0
 #define AST_LAYOUT_HWC 1
@@ -74,8 +75,9 @@ int ast_gram_tf32_supported(const float* F, int C, int64_t HW, int64_t ld);
 int ast_gram_mse_fwd(const float* F, int C, int64_t HW, int64_t ld, float scale, const float* A,
                      float* out, float* loss, void* ws, size_t ws_bytes, int precision,
                      void* stream);
-/* round_out != 0: `out` is stored rounded to nearest TF32 (the loss is still computed from the exact values).  Use it
- * when `out` = D only feeds ast_gram_bwd_nhwc(..., d_prerounded = 1): the backward's converter warps then skip D. */
+/* round_out = 1: `out` is stored rounded to nearest TF32 (the loss is still computed from the exact values).  Use it
+ * when `out` = D only feeds ast_gram_bwd_nhwc(..., d_prerounded = 1): the backward's converter warps then skip D.
+ * round_out = 2: `out` is stored as C*C bfloat16 (round to nearest even) for ast_gram_bwd_nhwc_bf16. */
 int ast_gram_finalize(const float* G_raw, int C, float scale, const float* A, float* out,
                       float* loss, void* ws, size_t ws_bytes, int round_out, void* stream);
 
@@ -119,6 +121,14 @@ int ast_gram_mse_fwd_nhwc(const float* F, int C, int64_t HW, float scale, const 
 int ast_gram_bwd_nhwc(const float* D, const float* F, int C, int64_t HW, float scale,
                       const float* gscale, float* dF, int accumulate, int d_prerounded,
                       int relu_mask, void* stream);
+
+/* BF16 operands (AST_PREC_BF16 — north_star: "TF32 or BF16 operands with FP32 accumulation") for the backward at the
+ * one tensor-bound width, C = 512: D_bf16 is (C, C) bfloat16 as written by ast_gram_mse_fwd_nhwc / ast_gram_finalize /
+ * ast_gram_finalize_batch with round_out = 2 (`out` then holds C*C bfloat16 instead of C*C float); the kernel rounds the
+ * staged fp32 feature tile to bfloat16 (cvt.rn) in shared memory.  Narrower layers are HBM-bound: use
+ * ast_gram_bwd_nhwc.  The forward contraction (the loss and D itself) always takes TF32 operands. */
+int ast_gram_bwd_nhwc_bf16(const void* D_bf16, const float* F, int C, int64_t HW, float scale,
+                           const float* gscale, float* dF, int accumulate, int relu_mask, void* stream);
 
 /* ---- Content MSE (neural_style_transfer.py:95) ---------------------------------------------
  *   *loss = scale * sum((X - T)^2)      (scale = 1/n for MSELoss(reduction='mean'))

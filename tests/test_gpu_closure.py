@@ -309,3 +309,29 @@ def test_two_concurrent_jobs_like_the_reference_executor(seeded_vgg):
         assert [k for _, k in s] == [k for _, k in t] == list(range(1, 9))
         for (a, _), (b, _) in zip(s, t):
             assert np.array_equal(a, b)
+
+
+def test_bf16_mode_closure_within_budget(golden, seeded_vgg):
+    """precision='bf16' (AST_PREC_BF16): forward contractions stay TF32 — the loss is bit-identical to the TF32 mode —
+    and the 512-channel backward takes bfloat16 operands: the image gradient stays inside a 5e-3 budget of the oracle."""
+    from artstyletransfer_b200 import math_utils, neural_style_transfer as nst
+    gd = golden('closure.npz')
+    out = {}
+    for prec in ('tf32', 'bf16'):
+        nst.PRECISION = prec
+        try:
+            net, cidx, sidx = math_utils.prepare_model('vgg19', dev())
+            out[prec] = product_closure(nst, net, cidx, sidx, [gd['content'], gd['content_l1']], [gd['style'], gd['style_l1']], gd['init'])
+        finally:
+            nst.PRECISION = None
+    assert out['bf16'][0] == out['tf32'][0]
+    onet, ocidx, osidx = O.make_vgg19(1234)
+    onet = onet.to(dev())
+    c_lv, s_lv = [gd['content'], gd['content_l1']], [gd['style'], gd['style_l1']]
+    targets = [O.torch_targets(onet, ocidx, osidx, torch.from_numpy(O.prepare_img(c)).to(dev()),
+                               torch.from_numpy(O.prepare_img(s)).to(dev())) for c, s in zip(c_lv, s_lv)]
+    ototal, _, ograd = O.torch_closure(onet, ocidx, osidx, targets, torch.from_numpy(O.prepare_img(gd['init'])).to(dev()), WEIGHTS)
+    assert abs(out['bf16'][0] - float(ototal)) / float(ototal) < 1e-4
+    e_bf, e_tf = rel(out['bf16'][2], ograd.cpu().numpy()), rel(out['tf32'][2], ograd.cpu().numpy())
+    print(f'image-gradient error vs oracle: tf32 {e_tf:.2e}, bf16 mode {e_bf:.2e}')
+    assert e_bf < 5e-3 and not np.array_equal(out['bf16'][2], out['tf32'][2])

@@ -220,3 +220,37 @@ def test_gram_finalize_batch_matches_single_finalize():
             assert torch.equal(d_b, d_s)
             if l_b is not None:
                 assert abs(float(l_b) - float(l_s)) <= 1e-6 * abs(float(l_s))
+
+
+@pytest.mark.parametrize('hw', [77, 1536, 2500, 24576])
+@pytest.mark.parametrize('mode', ['store', 'accumulate', 'relu'])
+def test_gram_bwd_bf16_c512_vs_oracle(hw, mode):
+    """AST_PREC_BF16: the C = 512 backward with bfloat16 operands (D from the finalize kernel with round_out = 2, the
+    feature tile rounded in shared memory), fp32 accumulation, against the float64 product of the EXACT operands
+    (tolerance: bf16 has 8 mantissa bits, errors average over K = 512) and against the float64 product of the
+    bf16-rounded operands (what the tensor core must compute: fp32-accumulation tight)."""
+    from artstyletransfer_b200 import ops
+    c = 512
+    f = _feat(c, hw, 41 + hw)
+    a = torch.rand((c, c), device=dev()) * 1e-3
+    a = ((a + a.t()) / 2).contiguous()
+    ws = ops.gram_workspace(c, hw, dev())
+    d32 = torch.empty((c, c), device=dev()); l32 = torch.empty((), device=dev())
+    dbf = torch.empty((c, c), dtype=torch.bfloat16, device=dev()); lbf = torch.empty((), device=dev())
+    ops.gram_mse_fwd_nhwc(f, c, hw, 1.0 / (c * hw), a, d32, l32, ws)
+    ops.gram_mse_fwd_nhwc(f, c, hw, 1.0 / (c * hw), a, dbf, lbf, ws, round_out=2)
+    assert l32.item() == lbf.item()                                   # the loss never sees the rounding
+    assert torch.equal(dbf, d32.to(torch.bfloat16))                   # round to nearest even, like torch
+    base = torch.randn((hw, c), device=dev()) * 1e-3
+    acc = mode != 'store'
+    g = base.clone() if acc else torch.full((hw, c), float('nan'), device=dev())
+    ops.gram_bwd_nhwc_auto(dbf, f, c, hw, 2.0, torch.tensor(0.5, device=dev()), g, acc, relu_mask=mode == 'relu')
+    exact = f.double() @ d32.double()
+    rounded = f.to(torch.bfloat16).double() @ dbf.double()
+    if acc:
+        exact, rounded = exact + base.double(), rounded + base.double()
+    if mode == 'relu':
+        exact, rounded = exact * (f > 0), rounded * (f > 0)
+    assert not torch.isnan(g).any()
+    assert rel(g.cpu().numpy(), rounded.cpu().numpy()) < 2e-5
+    assert rel(g.cpu().numpy(), exact.cpu().numpy()) < 6e-3
