@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libast_sm100.so')
 
-AST_ABI_VERSION = 6
+AST_ABI_VERSION = 7
 AST_PREC_TF32, AST_PREC_FP32, AST_PREC_BF16 = 0, 1, 2
 AST_LAYOUT_CHW, AST_LAYOUT_HWC = 0, 1
 AST_COORD_TORCH, AST_COORD_CV2 = 0, 1
@@ -76,6 +76,8 @@ SIGNATURES = {
     'ast_level_combine': (_i, [_p, _i, _p, _p, _f, _f, _f, _p, _p]),
     'ast_bicubic_down2x': (_i, [_p, _i, _i, _i, _p, _p]),
     'ast_bicubic_down2x_adj': (_i, [_p, _i, _i, _i, _p, _i, _p]),
+    'ast_bicubic_down2x_tv_workspace_bytes': (_sz, [_i, _i, _i]),
+    'ast_bicubic_down2x_tv': (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     'ast_bicubic_resize': (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p]),
     'ast_bicubic_resize_adj': (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     'ast_noise_init': (_i, [_p, _i, _i, C.POINTER(NoiseLevel), _i, _d, _i, _i, _d, _d, _p, _p]),

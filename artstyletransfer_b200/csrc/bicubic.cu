@@ -31,8 +31,20 @@ constexpr int D2_HALF = D2_TW + 4;             // 132 entries per parity per row
 //   O[r][k+1] = x[row r][2*(e0+k) - 1]  (odd  global columns), k = -1 .. 130
 // Output column e = e0+le reads O[le], E[le], O[le+1], E[le+1] = global columns 2e-1 .. 2e+2.
 
+// TV = true (ast_bicubic_down2x_tv): the block also sums |x[r,c] - x[r,c+1]| and |x[r,c] - x[r+1,c]| over the 32 x 256
+// input pixels it owns — they are all in the staged tile, neighbours included — so total_variation(x)
+// (math_utils.py:37-41) costs no pass of its own over the image the pyramid step reads anyway.  Per-block fp64 partials
+// go to the workspace; the last block (ticket) adds them in block order: deterministic.
+struct TvTileWs {
+  unsigned int ticket;
+  unsigned int pad[15];
+  double partials[1];       // [2][n_blocks]
+};
+
+template <bool TV>
 __global__ void __launch_bounds__(256) down2x_kernel(const float* __restrict__ x, int H, int W,
-                                                    float* __restrict__ y, int vec_ok) {
+                                                    float* __restrict__ y, int vec_ok, int C, float* __restrict__ sums2,
+                                                    float* __restrict__ tv, TvTileWs* __restrict__ ws) {
   __shared__ __align__(16) float tileE[D2_SROWS * D2_HALF];
   __shared__ __align__(16) float tileO[D2_SROWS * D2_HALF];
   const int Ho = H >> 1, Wo = W >> 1;
@@ -106,6 +118,54 @@ __global__ void __launch_bounds__(256) down2x_kernel(const float* __restrict__ x
     for (int k = 0; k < 8; ++k) {
       const int d = d0 + lr0 + k;
       if (d < Ho) yp[(size_t)d * Wo + e] = ((h[2 * k] * w0 + h[2 * k + 1] * w1) + h[2 * k + 2] * w1) + h[2 * k + 3] * w0;
+    }
+  }
+  if (TV) {
+    // this thread: input columns 2e, 2e+1 (E[le+2], O[le+2]; right neighbour E[le+3]) x input rows 2(d0+lr0) .. +15 =
+    // local rows 2*lr0+1 .. 2*lr0+16 (row below: +1, staged up to local row 33).  Out-of-image neighbours were
+    // staged as clamped copies (difference 0); out-of-image OWNERS (partial tiles) are masked.
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    float sx = 0.f, sy = 0.f;
+    const bool c0ok = 2 * e < W, c1ok = 2 * e + 1 < W;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int l = 2 * lr0 + 1 + r;
+      if (gr0 + l < H) {
+        const float e0v = tileE[l * D2_HALF + le + 2], o0v = tileO[l * D2_HALF + le + 2], e1v = tileE[l * D2_HALF + le + 3];
+        const float edn = tileE[(l + 1) * D2_HALF + le + 2], odn = tileO[(l + 1) * D2_HALF + le + 2];
+        if (c0ok) { sx += fabsf(e0v - o0v); sy += fabsf(e0v - edn); }
+        if (c1ok) { sx += fabsf(o0v - e1v); sy += fabsf(o0v - odn); }
+      }
+    }
+    const int nb = gridDim.x * gridDim.y * gridDim.z;
+    const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const double bx = block_sum((double)sx, red), by = block_sum((double)sy, red);
+    if (threadIdx.x == 0) {
+      ws->partials[bid] = bx;
+      ws->partials[nb + bid] = by;
+      __threadfence();
+      is_last = atomicAdd(&ws->ticket, 1u) == (unsigned)nb - 1u;
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      double ax = 0.0, ay = 0.0;
+      for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        ax += ((volatile double*)ws->partials)[i];
+        ay += ((volatile double*)ws->partials)[nb + i];
+      }
+      ax = block_sum(ax, red);
+      ay = block_sum(ay, red);
+      if (threadIdx.x == 0) {
+        sums2[0] = (float)ax;
+        sums2[1] = (float)ay;
+        if (tv) {
+          const double mx = ax / ((double)C * H * (W - 1)), my = ay / ((double)C * (H - 1) * W);
+          *tv = (float)(mx * mx + my * my);
+        }
+        ws->ticket = 0u;
+      }
     }
   }
 }
@@ -352,8 +412,30 @@ extern "C" int ast_bicubic_down2x(const float* x, int C, int H, int W, float* y,
   const int Ho = H / 2, Wo = W / 2;
   const int vec_ok = aligned16p(x) && (W % 4 == 0);
   dim3 grid((Wo + D2_TW - 1) / D2_TW, (Ho + D2_TH - 1) / D2_TH, C);
-  down2x_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, H, W, y, vec_ok);
+  down2x_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, H, W, y, vec_ok, C, nullptr, nullptr, nullptr);
   return check_launch("ast_bicubic_down2x");
+}
+
+extern "C" size_t ast_bicubic_down2x_tv_workspace_bytes(int C, int H, int W) {
+  if (C <= 0 || H < 2 || W < 2) return 0;
+  const size_t nb = (size_t)((W / 2 + D2_TW - 1) / D2_TW) * ((H / 2 + D2_TH - 1) / D2_TH) * C;
+  return 64 + 2 * nb * sizeof(double);
+}
+
+extern "C" int ast_bicubic_down2x_tv(const float* x, int C, int H, int W, float* y, float* sums2, float* tv, void* ws,
+                                     size_t ws_bytes, void* stream) {
+  AST_REQUIRE(x && y && sums2 && ws, AST_ERR_INVALID, "ast_bicubic_down2x_tv: null pointer");
+  AST_REQUIRE(C > 0 && H >= 2 && W >= 2, AST_ERR_INVALID, "ast_bicubic_down2x_tv: bad shape %dx%dx%d", C, H, W);
+  AST_REQUIRE((H % 2 == 0) && (W % 2 == 0), AST_ERR_UNSUPPORTED,
+              "ast_bicubic_down2x_tv: H and W must be even (got %dx%d)", H, W);
+  AST_REQUIRE(C <= 65535, AST_ERR_INVALID, "ast_bicubic_down2x_tv: too many planes");
+  AST_REQUIRE(ws_bytes >= ast_bicubic_down2x_tv_workspace_bytes(C, H, W) && aligned16p(ws), AST_ERR_WORKSPACE,
+              "ast_bicubic_down2x_tv: workspace %zu < %zu", ws_bytes, ast_bicubic_down2x_tv_workspace_bytes(C, H, W));
+  const int Ho = H / 2, Wo = W / 2;
+  const int vec_ok = aligned16p(x) && (W % 4 == 0);
+  dim3 grid((Wo + D2_TW - 1) / D2_TW, (Ho + D2_TH - 1) / D2_TH, C);
+  down2x_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, H, W, y, vec_ok, C, sums2, tv, (TvTileWs*)ws);
+  return check_launch("ast_bicubic_down2x_tv");
 }
 
 extern "C" int ast_bicubic_down2x_adj(const float* gy, int C, int H, int W, float* gx, int accumulate,

@@ -257,6 +257,7 @@ class LevelPathFn(torch.autograd.Function):
     def forward(ctx, cfg, img):
         plan, targets, content_idx, style_idx, weights, wss = cfg[:6]
         bf16 = bool(cfg[6]) if len(cfg) > 6 else False
+        tv_pre = cfg[7] if len(cfg) > 7 else None      # (sums2, tv) from the fused pyramid step that read this image
         dev = ops._require_cuda(img)
         cw, sw, tvw = (float(v) for v in weights)
         img = img.contiguous()
@@ -277,10 +278,14 @@ class LevelPathFn(torch.autograd.Function):
         if xc.numel() != targets.content_cl.numel():
             raise ValueError('content feature map and target differ in size')
         ops.mse_fwd(xc, targets.content_cl, 1.0 / xc.numel(), vals[n_style], wss.for_reduce('content', dev))
-        sums2 = torch.empty(2, dtype=torch.float32, device=dev)
-        ops.tv_fwd(img, sums2, vals[n_style + 1], wss.for_reduce('tv', dev))
+        if tv_pre is not None:
+            sums2, tv_val = tv_pre
+        else:
+            sums2 = torch.empty(2, dtype=torch.float32, device=dev)
+            tv_val = vals[n_style + 1]
+            ops.tv_fwd(img, sums2, tv_val, wss.for_reduce('tv', dev))
         ops._launch(dev, ('combine',), 'ast_level_combine', vals.data_ptr(), n_style, vals[n_style].data_ptr(),
-                    vals[n_style + 1].data_ptr(), cw, sw, tvw, out4.data_ptr())
+                    tv_val.data_ptr(), cw, sw, tvw, out4.data_ptr())
         if need_grad:
             ctx.save_for_backward(img)
             ctx.pack = (plan, targets, content_idx, tuple(style_idx), (cw, sw, tvw), saved, ds, sums2)

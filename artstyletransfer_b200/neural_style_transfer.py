@@ -57,6 +57,9 @@ GRAPH_CLOSURE = os.environ.get('AST_CUDA_GRAPH', '1') != '0'
 GRAPH_STRICT = os.environ.get('AST_CUDA_GRAPH') == '1' or os.environ.get('AST_CUDA_GRAPH_STRICT', '0') == '1'
 GRAPH_WARMUP = 2
 FUSED_ADAM = os.environ.get('AST_FUSED_ADAM', '1') != '0'
+# True: the bicubic pyramid step that reads a level's image also computes that level's total variation
+# (ast_bicubic_down2x_tv): one pass over every image but the smallest instead of two.
+FUSED_PYRAMID_TV = os.environ.get('AST_FUSED_PYRAMID_TV', '1') != '0'
 # True: process() takes the per-step image snapshot (:207-208) off the critical path — one fused unprepare kernel into
 # a device staging buffer, the device->host copy on a side stream into page-locked memory, and the NEXT optimizer
 # step is enqueued before the copy is awaited, so the GPU never idles on the yield.  The sequence of yielded
@@ -159,7 +162,13 @@ class LossBuilder:
             return None
         return feature_path.plan_for(self.__neural_net)
 
-    def build(self, optimizing_img):
+    @property
+    def workspaces(self):
+        return self.__wss
+
+    def build(self, optimizing_img, _tv=None):
+        """_tv (internal): (sums2, tv) of optimizing_img already computed by the fused pyramid step
+        (ops.bicubic_half_tv) — the level then skips its own total-variation pass."""
         if self.shard is not None:
             return self.shard.build(optimizing_img)
         if self.replicated_rank0_only and torch.is_grad_enabled():
@@ -174,7 +183,7 @@ class LossBuilder:
             cfg = (plan, self.__path_targets, self.__content_feature_maps_index,
                    tuple(self.__style_feature_maps_indices),
                    (self.__content_weight, self.__style_weight, self.__tv_weight), self.__wss,
-                   ops._prec(PRECISION) == ops.L.AST_PREC_BF16)
+                   ops._prec(PRECISION) == ops.L.AST_PREC_BF16, _tv)
             return feature_path.LevelPathFn.apply(cfg, optimizing_img)
         feats = self.__neural_net(optimizing_img)
         cfg = (self.__target_content_representation, self.__target_grams,
@@ -245,13 +254,24 @@ class _Job:
             # every level is row-band sharded: all levels in lock-step, grouped halo exchanges (sharded_path.py)
             total_loss = self.pyramid.evaluate(optimizing_img)
             loss_builders = []
+        # lower resolutions of optimizing_img: chained bicubic 2x down (:168-176).  The whole chain first: the step that
+        # reads level i-1 to produce level i also hands back total_variation(level i-1), which level i-1's loss needs
+        tvs = [None] * len(loss_builders)
         for i in range(len(loss_builders)):
-            # lower resolutions of optimizing_img: chained bicubic 2x down (:168-176)
             if i == 0:
                 optimizing_img_levels = [optimizing_img]
+                continue
+            prev = optimizing_img_levels[i - 1]
+            fused = (FUSED_PYRAMID_TV and prev.shape[-2] % 2 == 0 and prev.shape[-1] % 2 == 0
+                     and loss_builders[i - 1].path_plan(prev) is not None and loss_builders[i - 1].shard is None)
+            if fused:
+                nxt, sums2, tv = ops.bicubic_half_tv(prev, loss_builders[i - 1].workspaces)
+                tvs[i - 1] = (sums2, tv)
             else:
-                optimizing_img_levels.append(ops.bicubic_half(optimizing_img_levels[i - 1]))
-            total_loss_l, content_loss, style_loss, tv_loss = loss_builders[i].build(optimizing_img_levels[i])
+                nxt = ops.bicubic_half(prev)
+            optimizing_img_levels.append(nxt)
+        for i in range(len(loss_builders)):
+            total_loss_l, content_loss, style_loss, tv_loss = loss_builders[i].build(optimizing_img_levels[i], _tv=tvs[i])
             if total_loss is None:
                 total_loss = total_loss_l
             else:

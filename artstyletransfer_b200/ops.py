@@ -68,7 +68,7 @@ STATS = KernelStats()
 
 # kernels launched per C-ABI entry point
 _KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_mse_fwd_nhwc': 2, 'ast_gram_bwd_nhwc': 1, 'ast_gram_bwd_nhwc_bf16': 1, 'ast_gram_finalize': 1, 'ast_gram_finalize_batch': 1, 'ast_gram_bwd': 1, 'ast_mse_fwd': 1, 'ast_mse_bwd': 1,
-                     'ast_tv_fwd': 1, 'ast_tv_bwd': 1, 'ast_level_combine': 1, 'ast_bicubic_down2x': 1,
+                     'ast_tv_fwd': 1, 'ast_tv_bwd': 1, 'ast_level_combine': 1, 'ast_bicubic_down2x': 1, 'ast_bicubic_down2x_tv': 1,
                      'ast_bicubic_down2x_adj': 1, 'ast_bicubic_resize': 1, 'ast_bicubic_resize_adj': 1,
                      'ast_noise_init': 1, 'ast_bias_relu_nhwc': 1, 'ast_relu_bwd': 1, 'ast_maxpool2x2_nhwc': 1,
                      'ast_maxpool2x2_bwd_nhwc': 1, 'ast_chw_to_hwc': 1, 'ast_hwc_to_chw': 1, 'ast_unprepare_hwc': 1, 'ast_halo_exchange': 1}
@@ -491,6 +491,24 @@ def bicubic_down_raw(x: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
     return y
 
 
+def bicubic_down_tv_raw(x: torch.Tensor, wss: 'LevelWorkspaces'):
+    """Exact 2x down-sampling of (..., H, W) (even H, W) fused with total_variation(x): returns (y, sums2, tv) where
+    sums2 / tv are what tv_fwd(x) would have produced — one pass over x instead of two."""
+    _require_cuda(x)
+    x = x.contiguous()
+    c, h, w = _planes(x)
+    if h % 2 or w % 2:
+        raise ValueError(f'fused pyramid step + TV needs even sizes; got {h}x{w}')
+    dev = x.device
+    y = torch.empty(x.shape[:-2] + (h // 2, w // 2), dtype=torch.float32, device=dev)
+    sums2 = torch.empty(2, dtype=torch.float32, device=dev)
+    tv = torch.empty((), dtype=torch.float32, device=dev)
+    ws = wss.for_named('down_tv', L.load().ast_bicubic_down2x_tv_workspace_bytes(c, h, w), dev)
+    _launch(dev, ('down2x_tv', c, h, w), 'ast_bicubic_down2x_tv', x.data_ptr(), c, h, w, y.data_ptr(), sums2.data_ptr(),
+            tv.data_ptr(), ws.ptr, ws.nbytes)
+    return y, sums2, tv
+
+
 def bicubic_down_adj_raw(gy: torch.Tensor, in_h: int, in_w: int, gx: Optional[torch.Tensor] = None,
                          accumulate: bool = False) -> torch.Tensor:
     _require_cuda(gy)
@@ -523,6 +541,26 @@ class BicubicHalfFn(torch.autograd.Function):
 
 def bicubic_half(x: torch.Tensor) -> torch.Tensor:
     return BicubicHalfFn.apply(x)
+
+
+class BicubicHalfTvFn(torch.autograd.Function):
+    """bicubic_half(x) that also returns total_variation(x)'s two sums and value (non-differentiable by-products: the
+    TV term's gradient is taken by the level's loss node from sums2, as before)."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, wss):
+        ctx.in_hw = (x.shape[-2], x.shape[-1])
+        y, sums2, tv = bicubic_down_tv_raw(x, wss)
+        ctx.mark_non_differentiable(sums2, tv)
+        return y, sums2, tv
+
+    @staticmethod
+    def backward(ctx, gy, g_sums2, g_tv):
+        return bicubic_down_adj_raw(gy, *ctx.in_hw), None
+
+
+def bicubic_half_tv(x: torch.Tensor, wss: 'LevelWorkspaces'):
+    return BicubicHalfTvFn.apply(x, wss)
 
 
 def bicubic_resize(x: torch.Tensor, out_h: int, out_w: int, layout: str = 'chw', coord: str = 'cv2') -> torch.Tensor:
@@ -560,6 +598,12 @@ class LevelWorkspaces:
         ws = self.gram.get(k)
         if ws is None or ws.nbytes < need or ws.buf.device != dev:
             ws = self.gram[k] = Workspace(need, dev)
+        return ws
+
+    def for_named(self, name: str, nbytes: int, dev: torch.device) -> Workspace:
+        ws = self.gram.get(name)
+        if ws is None or ws.nbytes < nbytes or ws.buf.device != dev:
+            ws = self.gram[name] = Workspace(nbytes, dev)
         return ws
 
     def for_reduce(self, which: str, dev: torch.device) -> Workspace:

@@ -37,6 +37,7 @@ MULTI_STREAM = os.environ.get('AST_LEVEL_STREAMS', '1') != '0'
 # separate bias + ReLU pass (8 B per activation element, 3 ms of an unsharded L=3 closure).  '0': the convolution
 # writes the owned rows through cudnn_convolution.out into a persistent band, ast_bias_relu_nhwc follows.
 FUSED_BAND_CONV = os.environ.get('AST_SHARD_FUSED_CONV', '1') != '0'
+FUSED_PYRAMID_TV = os.environ.get('AST_FUSED_PYRAMID_TV', '1') != '0'
 
 
 class Lanes:
@@ -222,9 +223,16 @@ class PyramidFn(torch.autograd.Function):
     def forward(ctx, pyr: ShardedPyramid, img):
         ops._require_cuda(img)
         imgs = [img.contiguous()]
+        tvs = [None] * len(pyr.levels)
         for i in range(1, len(pyr.levels)):
-            imgs.append(ops.bicubic_down_raw(imgs[-1], imgs[-1].shape[-2] // 2, imgs[-1].shape[-1] // 2))
-        out4s, state = pyramid_forward(pyr.levels, imgs, pyr.lanes)
+            prev = imgs[-1]
+            if FUSED_PYRAMID_TV and prev.shape[-2] % 2 == 0 and prev.shape[-1] % 2 == 0:
+                nxt, sums2, tv = ops.bicubic_down_tv_raw(prev, pyr.levels[i - 1].wss)   # + total_variation(prev)
+                tvs[i - 1] = (sums2, tv)
+            else:
+                nxt = ops.bicubic_down_raw(prev, prev.shape[-2] // 2, prev.shape[-1] // 2)
+            imgs.append(nxt)
+        out4s, state = pyramid_forward(pyr.levels, imgs, pyr.lanes, tvs)
         total = out4s[0][0]
         for o in out4s[1:]:
             total = 1.0 * total + o[0]
@@ -244,7 +252,8 @@ class PyramidFn(torch.autograd.Function):
         return None, d_imgs[0]
 
 
-def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Tensor], lanes: Lanes = _SERIAL):
+def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Tensor], lanes: Lanes = _SERIAL,
+                    tvs: Sequence = None):
     """Forward schedule of several sharded levels in lock-step (one level = the plain sharded level).
     Returns ([out4 per level], state for pyramid_backward)."""
     dev = ops._require_cuda(*imgs)
@@ -348,10 +357,14 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
         cw, sw, tvw = sh.weights
         n_style = len(sh.sidx)
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
-        sums2 = torch.empty(2, dtype=torch.float32, device=dev)
-        ops.tv_fwd(im, sums2, vals[n_style], sh.wss.for_reduce('tv', dev))
+        if tvs is not None and tvs[li] is not None:        # the fused pyramid step already has total_variation(im)
+            sums2, tv_val = tvs[li]
+        else:
+            sums2 = torch.empty(2, dtype=torch.float32, device=dev)
+            tv_val = vals[n_style]
+            ops.tv_fwd(im, sums2, tv_val, sh.wss.for_reduce('tv', dev))
         ops._launch(dev, ('combine',), 'ast_level_combine', vals.data_ptr(), n_style, packed[sh.content_slot].data_ptr(),
-                    vals[n_style].data_ptr(), cw, sw, tvw, out4.data_ptr())
+                    tv_val.data_ptr(), cw, sw, tvw, out4.data_ptr())
         out4s.append(out4)
         per_level.append((sh, sh.generation, ds_all[li], im, sums2))
     return out4s, per_level

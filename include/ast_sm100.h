@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 6
+#define AST_ABI_VERSION 7
 
 #define AST_OK               0
 #define AST_ERR_INVALID     -1   /* bad argument (null pointer, non-positive size, misalignment) */
@@ -216,6 +216,13 @@ int ast_level_combine(const float* style_mse, int n_style, const float* content,
 int ast_bicubic_down2x(const float* x, int C, int H, int W, float* y, void* stream);
 int ast_bicubic_down2x_adj(const float* gy, int C, int H, int W, float* gx, int accumulate,
                            void* stream);
+/* The pyramid step AND total_variation(x) (math_utils.py:37-41, evaluated on every level at
+ * neural_style_transfer.py:107) in one pass over x: every pixel and its right / lower neighbour are in the tile the
+ * resampler stages anyway.  sums2 / tv as ast_tv_fwd writes them (feed sums2 to ast_tv_bwd).  ws:
+ * ast_bicubic_down2x_tv_workspace_bytes(C, H, W) bytes, zero-filled once, reusable. */
+size_t ast_bicubic_down2x_tv_workspace_bytes(int C, int H, int W);
+int ast_bicubic_down2x_tv(const float* x, int C, int H, int W, float* y, float* sums2, float* tv,
+                          void* ws, size_t ws_bytes, void* stream);
 /* General ratio (odd pyramid sizes; cv2.resize(..., INTER_CUBIC) at
  * neural_style_transfer.py:226, :304, :427).  The adjoint is CHW only. */
 int ast_bicubic_resize(const float* x, int C, int Hin, int Win, float* y, int Hout, int Wout,

@@ -189,3 +189,32 @@ def test_cpu_tensor_is_rejected():
         math_utils.total_variation(torch.zeros(1, 3, 8, 8))
     with pytest.raises(RuntimeError, match='CUDA'):
         math_utils.gram_matrix(torch.zeros(1, 64, 8, 8))
+
+
+@pytest.mark.parametrize('c,h,w', [(3, 256, 384), (3, 50, 70), (3, 34, 516), (1, 2, 2), (3, 2048, 3072), (2, 130, 258)])
+def test_fused_pyramid_step_and_tv(c, h, w):
+    """ast_bicubic_down2x_tv == ast_bicubic_down2x (bit for bit) + ast_tv_fwd of the same image (the sums are added in
+    a different order: 1e-6), including partial tiles, unaligned widths and a reused workspace."""
+    from artstyletransfer_b200 import ops
+    dev = torch.device('cuda', 0)
+    g = torch.Generator(device='cuda').manual_seed(h * 1000 + w)
+    wss = ops.LevelWorkspaces()
+    for rep in range(2):
+        x = (torch.rand((1, c, h, w), generator=g, device=dev) * 255 - 120).contiguous()
+        y_ref = ops.bicubic_down_raw(x, h // 2, w // 2)
+        sums_ref = torch.empty(2, device=dev); tv_ref = torch.empty((), device=dev)
+        ops.tv_fwd(x, sums_ref, tv_ref, ops.reduce_workspace(dev))
+        y, sums2, tv = ops.bicubic_down_tv_raw(x, wss)
+        assert torch.equal(y, y_ref)
+        ref64 = [(x[..., :-1] - x[..., 1:]).double().abs().sum().item(), (x[..., :-1, :] - x[..., 1:, :]).double().abs().sum().item()]
+        np.testing.assert_allclose(sums2.cpu().numpy(), ref64, rtol=2e-6)
+        np.testing.assert_allclose(sums2.cpu().numpy(), sums_ref.cpu().numpy(), rtol=2e-6)
+        if h > 2 and w > 2:
+            assert abs(float(tv) - float(tv_ref)) <= 4e-6 * abs(float(tv_ref))
+    # autograd wrapper: same gradient as the unfused step
+    x1 = x.clone().requires_grad_(True); x2 = x.clone().requires_grad_(True)
+    ya, _, _ = ops.bicubic_half_tv(x1, wss)
+    yb = ops.bicubic_half(x2)
+    u = torch.randn_like(ya)
+    (ya * u).sum().backward(); (yb * u).sum().backward()
+    assert torch.equal(x1.grad, x2.grad)
