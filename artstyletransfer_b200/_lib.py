@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libast_sm100.so')
 
-AST_ABI_VERSION = 7
+AST_ABI_VERSION = 8
 AST_PREC_TF32, AST_PREC_FP32, AST_PREC_BF16 = 0, 1, 2
 AST_LAYOUT_CHW, AST_LAYOUT_HWC = 0, 1
 AST_COORD_TORCH, AST_COORD_CV2 = 0, 1
@@ -44,6 +44,17 @@ class FinalizeItem(C.Structure):
 
 AST_HALO_MAX_ROWS = 16
 AST_FINALIZE_MAX_ITEMS = 32
+AST_GATHER_MAX_PEERS = 7
+AST_GATHER_MAX_SEGS = 24
+
+
+class BandGatherDesc(C.Structure):
+    """struct ast_band_gather_desc (include/ast_sm100.h)."""
+    _fields_ = [('local_base', C.c_void_p), ('peer_base', C.c_void_p * AST_GATHER_MAX_PEERS),
+                ('ready_remote', C.c_void_p * AST_GATHER_MAX_PEERS), ('ready_local', C.c_void_p * AST_GATHER_MAX_PEERS),
+                ('arrive_remote', C.c_void_p * AST_GATHER_MAX_PEERS), ('arrive_local', C.c_void_p * AST_GATHER_MAX_PEERS),
+                ('state', C.c_void_p), ('seg_off', C.c_int64 * AST_GATHER_MAX_SEGS),
+                ('seg_bytes', C.c_int64 * AST_GATHER_MAX_SEGS), ('n_peers', C.c_int32), ('n_segs', C.c_int32)]
 _p, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 
 # name -> (restype, argtypes); one entry per declaration in include/ast_sm100.h
@@ -82,6 +93,8 @@ SIGNATURES = {
     'ast_bicubic_resize_adj': (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     'ast_noise_init': (_i, [_p, _i, _i, C.POINTER(NoiseLevel), _i, _d, _i, _i, _d, _d, _p, _p]),
     'ast_halo_exchange': (_i, [C.POINTER(HaloRow), _i, _p]),
+    'ast_band_announce': (_i, [C.POINTER(BandGatherDesc), _p]),
+    'ast_band_gather': (_i, [C.POINTER(BandGatherDesc), _p]),
 }
 
 _lib = None

@@ -286,7 +286,8 @@ class _Job:
         if total_loss.requires_grad:
             total_loss.backward()
         if torch.is_grad_enabled():
-            _parallel.sync_image_grad(optimizing_img)
+            gathered = self.pyramid is not None and not VERBOSE and getattr(self.pyramid, 'gather', None) is not None
+            _parallel.sync_image_grad(optimizing_img, already_global=gathered)
         return total_loss
 
     def _graph_eligible(self):

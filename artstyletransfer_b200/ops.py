@@ -71,7 +71,7 @@ _KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_mse_fwd_nhwc': 2, 'ast_gra
                      'ast_tv_fwd': 1, 'ast_tv_bwd': 1, 'ast_level_combine': 1, 'ast_bicubic_down2x': 1, 'ast_bicubic_down2x_tv': 1,
                      'ast_bicubic_down2x_adj': 1, 'ast_bicubic_resize': 1, 'ast_bicubic_resize_adj': 1,
                      'ast_noise_init': 1, 'ast_bias_relu_nhwc': 1, 'ast_relu_bwd': 1, 'ast_maxpool2x2_nhwc': 1,
-                     'ast_maxpool2x2_bwd_nhwc': 1, 'ast_chw_to_hwc': 1, 'ast_hwc_to_chw': 1, 'ast_unprepare_hwc': 1, 'ast_halo_exchange': 1}
+                     'ast_maxpool2x2_bwd_nhwc': 1, 'ast_chw_to_hwc': 1, 'ast_hwc_to_chw': 1, 'ast_unprepare_hwc': 1, 'ast_halo_exchange': 1, 'ast_band_announce': 1, 'ast_band_gather': 1}
 
 
 def _launch(dev: torch.device, key, name: str, *args) -> None:

@@ -310,6 +310,81 @@ class PeerHaloGroup(TorchDistGroup):
         ops._launch(dev, ('halo_exchange', len(rows)), 'ast_halo_exchange', arr, len(rows))
 
 
+class PeerGradGather:
+    """The image-gradient pyramid of a row-band sharded job in NVLink peer memory (ast_band_gather, csrc/halo.cu).
+
+    Every rank keeps one gradient tensor per pyramid level in a SYMMETRIC buffer (torch symmetric memory: same layout
+    on every rank, peer-mapped), writes the rows it owns there, and `gather()` stores them into the same place of every
+    peer's buffer and waits for theirs: the rows of different ranks are disjoint, so no reduction — and no 75 MB NCCL
+    all-reduce — is needed; afterwards all ranks hold bit-identical gradients.  `announce()` at the start of a closure
+    tells the peers that this rank's buffer may be overwritten (its previous gradient has been consumed)."""
+
+    def __init__(self, group, device: torch.device, sizes, bands):
+        """sizes: [(H, W)] per level; bands: [(r0, r1)] rows this rank owns per level.  Collective."""
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib as L
+        self.rank, self.world = group.rank, group.world
+        if self.world - 1 > L.AST_GATHER_MAX_PEERS:
+            raise ValueError(f'peer-memory gradient gather supports {L.AST_GATHER_MAX_PEERS + 1} ranks')
+        offs, o = [], 0
+        for h, w in sizes:
+            offs.append(o)
+            o += (3 * h * w * 4 + 255) // 256 * 256
+        flags_off = o
+        total = flags_off + 256 * 2 * self.world
+        enable = getattr(symm_mem, 'enable_symm_mem_for_group', None)
+        if enable is not None:
+            try:
+                enable(dist.group.WORLD.group_name)
+            except Exception:
+                pass
+        self._buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self._hdl = symm_mem.rendezvous(self._buf, dist.group.WORLD)
+        ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        self._buf.zero_()
+        self._state = torch.zeros(32, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier()
+        self.views = [self._buf[offs[i]:offs[i] + 3 * h * w * 4].view(torch.float32).view(1, 3, h, w)
+                      for i, (h, w) in enumerate(sizes)]
+        d = L.BandGatherDesc()
+        d.local_base = ptrs[self.rank]
+        peers = [r for r in range(self.world) if r != self.rank]
+        for k, r in enumerate(peers):
+            d.peer_base[k] = ptrs[r]
+            # ready[src] at flags + 256 * src, arrive[src] at flags + 256 * (world + src) of the OWNER's buffer
+            d.ready_remote[k] = ptrs[r] + flags_off + 256 * self.rank
+            d.ready_local[k] = ptrs[self.rank] + flags_off + 256 * r
+            d.arrive_remote[k] = ptrs[r] + flags_off + 256 * (self.world + self.rank)
+            d.arrive_local[k] = ptrs[self.rank] + flags_off + 256 * (self.world + r)
+        d.state = self._state.data_ptr()
+        d.n_peers = len(peers)
+        n = 0
+        for i, ((h, w), (r0, r1)) in enumerate(zip(sizes, bands)):
+            if r1 <= r0:
+                continue
+            for c in range(3):
+                if n >= L.AST_GATHER_MAX_SEGS:
+                    raise ValueError('too many gradient segments for ast_band_gather')
+                d.seg_off[n] = offs[i] + (c * h + r0) * w * 4
+                d.seg_bytes[n] = (r1 - r0) * w * 4
+                if d.seg_off[n] % 16 or d.seg_bytes[n] % 16:
+                    raise ValueError('gradient rows must be 16-byte aligned (level widths multiples of 4)')
+                n += 1
+        d.n_segs = n
+        self._desc = d
+        self._device = device
+
+    def announce(self) -> None:
+        from . import ops
+        ops._launch(self._device, ('band_announce',), 'ast_band_announce', self._desc)
+
+    def gather(self) -> None:
+        from . import ops
+        ops._launch(self._device, ('band_gather', self._desc.n_segs), 'ast_band_gather', self._desc)
+
+
 def halo_exchange(group, rows, zero_border: bool = False) -> None:
     """rows: one (h + 2, w, C) contiguous view of a padded band, or a list of them (row 0 and row h+1 are the
     halos); a list entry may also be (view, up, dn[, level]) naming the ranks that own the rows above / below this
@@ -561,9 +636,10 @@ def lockstep_pyramid(loss_builders):
     return None
 
 
-def sync_image_grad(optimizing_img) -> None:
-    """All-reduce(sum) of the image gradient so that every rank steps an identical optimizer."""
-    if _GROUP is None or _GROUP.world == 1:
+def sync_image_grad(optimizing_img, already_global: bool = False) -> None:
+    """All-reduce(sum) of the image gradient so that every rank steps an identical optimizer.  already_global: the
+    closure gathered the gradient itself (PeerGradGather): nothing to do."""
+    if _GROUP is None or _GROUP.world == 1 or already_global:
         return
     if optimizing_img.grad is None:          # every rank must join the collective
         optimizing_img.grad = torch.zeros_like(optimizing_img)

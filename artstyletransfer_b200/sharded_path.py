@@ -38,6 +38,9 @@ MULTI_STREAM = os.environ.get('AST_LEVEL_STREAMS', '1') != '0'
 # writes the owned rows through cudnn_convolution.out into a persistent band, ast_bias_relu_nhwc follows.
 FUSED_BAND_CONV = os.environ.get('AST_SHARD_FUSED_CONV', '1') != '0'
 FUSED_PYRAMID_TV = os.environ.get('AST_FUSED_PYRAMID_TV', '1') != '0'
+# '1': every tap's partial Grams (all levels) are all-reduced as soon as they exist, on a side stream under the
+# convolutions above the tap; '0': one all-reduce of the whole packed buffer after the forward (round 1).
+OVERLAP_GRAM_ALLREDUCE = os.environ.get('AST_OVERLAP_GRAM_ALLREDUCE', '1') != '0'
 
 
 class Lanes:
@@ -208,6 +211,14 @@ class ShardedPyramid:
     def __init__(self, levels: List[ShardedPathLevel]):
         self.levels = list(levels)
         self.lanes = Lanes(levels[0].device, len(levels)) if MULTI_STREAM else _SERIAL
+        self.comm = torch.cuda.Stream(levels[0].device)          # the partial-Gram all-reduces (pyramid_forward)
+        # image gradient: an all-gather of the ranks' disjoint rows through NVLink peer memory instead of an all-reduce
+        # of the whole image — with the peer-memory group (AST_HALO=peer) unless AST_GRAD_GATHER=0
+        self.gather = None
+        grp = levels[0].group
+        if isinstance(grp, par.PeerHaloGroup) and grp.world > 1 and os.environ.get('AST_GRAD_GATHER', '1') != '0':
+            self.gather = par.PeerGradGather(grp, levels[0].device, [(sh.H, sh.W) for sh in levels],
+                                             [(sh.r0, sh.r1) for sh in levels])
 
     def evaluate(self, optimizing_img: torch.Tensor):
         """image leaf -> summed loss over the levels (neural_style_transfer.py:168-185), differentiable."""
@@ -222,6 +233,8 @@ class PyramidFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pyr: ShardedPyramid, img):
         ops._require_cuda(img)
+        if pyr.gather is not None and ctx.needs_input_grad[1]:
+            pyr.gather.announce()                  # my previous gradient has been consumed: peers may overwrite it
         imgs = [img.contiguous()]
         tvs = [None] * len(pyr.levels)
         for i in range(1, len(pyr.levels)):
@@ -232,7 +245,7 @@ class PyramidFn(torch.autograd.Function):
             else:
                 nxt = ops.bicubic_down_raw(prev, prev.shape[-2] // 2, prev.shape[-1] // 2)
             imgs.append(nxt)
-        out4s, state = pyramid_forward(pyr.levels, imgs, pyr.lanes, tvs)
+        out4s, state = pyramid_forward(pyr.levels, imgs, pyr.lanes, tvs, getattr(pyr, 'comm', None))
         total = out4s[0][0]
         for o in out4s[1:]:
             total = 1.0 * total + o[0]
@@ -240,20 +253,24 @@ class PyramidFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             ctx.state = state
             ctx.lanes = pyr.lanes
+            ctx.gather = pyr.gather
             ctx.shapes = [tuple(t.shape[-2:]) for t in imgs]
         return total
 
     @staticmethod
     def backward(ctx, g_total):
         state, ctx.state = ctx.state, None
-        d_imgs = pyramid_backward(state, g_total, ctx.lanes)
+        d_imgs = pyramid_backward(state, g_total, ctx.lanes, getattr(ctx, 'gather', None))
         for i in range(len(d_imgs) - 1, 0, -1):          # adjoint of the down-sampling chain, coarse -> fine
             ops.bicubic_down_adj_raw(d_imgs[i], *ctx.shapes[i - 1], gx=d_imgs[i - 1], accumulate=True)
-        return None, d_imgs[0]
+        g0 = d_imgs[0]
+        if getattr(ctx, 'gather', None) is not None:
+            g0 = g0.view(g0.shape)      # a fresh tensor object over the symmetric buffer: autograd can adopt it as .grad without a copy
+        return None, g0
 
 
 def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Tensor], lanes: Lanes = _SERIAL,
-                    tvs: Sequence = None):
+                    tvs: Sequence = None, comm: 'torch.cuda.Stream' = None):
     """Forward schedule of several sharded levels in lock-step (one level = the plain sharded level).
     Returns ([out4 per level], state for pyramid_backward)."""
     dev = ops._require_cuda(*imgs)
@@ -276,6 +293,53 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
     active = [li for li, sh in enumerate(levels) if sh.hb]       # the levels this rank owns rows of
     xs = [sh.xin for sh in levels]
     taps = [[None] * len(plan.tap_step) for _ in levels]
+    # Raw partial Grams + partial content MSE of every level, TAP-MAJOR: [relu1_1 of all levels | relu2_1 ... | relu5_1
+    # of all levels | content of all levels] (every slot 16-byte aligned).  The slots of one tap are one contiguous
+    # block, all-reduced as soon as that tap's partial Grams exist — on the `comm` stream, under the convolutions of the
+    # layers above it (OVERLAP_GRAM_ALLREDUCE); only the last block (relu5_1 + content, ~4 MB at L=3) is exposed.  Every
+    # rank finalises identically afterwards.
+    sidx0, cidx0 = sh0.sidx, sh0.cidx
+    for sh in levels:
+        if sh.sidx != sidx0 or sh.cidx != cidx0:
+            raise ValueError('lock-step levels must tap the same layers')
+    pad4 = lambda n: (n + 3) // 4 * 4
+    tap_off, o = [], 0
+    for j in range(len(sidx0)):
+        tap_off.append(o)
+        o += sum(pad4(sh.channels[j] ** 2) for sh in levels)
+    content_off = o
+    n_packed = o + pad4(len(levels))
+    packed_all = torch.zeros(n_packed, dtype=torch.float32, device=dev)
+    gram_slot, content_slot = [[None] * len(sidx0) for _ in levels], []
+    for j in range(len(sidx0)):
+        o = tap_off[j]
+        for li, sh in enumerate(levels):
+            c2 = sh.channels[j] ** 2
+            gram_slot[li][j] = packed_all[o:o + c2]
+            o += pad4(c2)
+    for li in range(len(levels)):
+        content_slot.append(packed_all[content_off + li:content_off + li + 1])
+    overlap = comm is not None and OVERLAP_GRAM_ALLREDUCE
+    main = torch.cuda.current_stream(dev)
+    pending = []                                   # completion events of the all-reduces in flight on `comm`
+
+    def all_reduce_block(lo, hi, last):
+        """Sum packed_all[lo:hi] over the ranks; every rank calls this for the same blocks in the same order."""
+        block = packed_all[lo:hi]
+        with ops.timed(dev, ('allreduce_packed_grams', hi - lo)):
+            if overlap and not last:
+                ready = torch.cuda.Event()
+                ready.record(main)
+                comm.wait_event(ready)
+                with torch.cuda.stream(comm):
+                    grp.all_reduce_sum(block)
+                    done = torch.cuda.Event()
+                    done.record(comm)
+                pending.append(done)
+            else:
+                grp.all_reduce_sum(block)
+
+    reduced_to = 0                                 # packed_all[:reduced_to] has been handed to an all-reduce
     for sidx in range(plan.n_steps_needed):
         st = plan.steps[sidx]
         if st[0] == 'conv' and sidx > 0:
@@ -301,37 +365,36 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
             else:
                 ops.maxpool2x2(_interior(x), _interior(y))
             for k in plan.taps_at.get(sidx, ()):
-                taps[li][k] = _interior(y)
+                tap = taps[li][k] = _interior(y)
+                if k in sh.sidx:                    # this band's partial Gram of the tap, straight into its slot
+                    j = sh.sidx.index(k)
+                    c, hw_band = tap.shape[1], tap.shape[2] * tap.shape[3]
+                    ops.gram_mse_fwd_nhwc(tap, c, hw_band, 1.0, None, gram_slot[li][j], None,
+                                          sh.wss.for_gram(j, c, hw_band, dev))
+                if k == sh.cidx:
+                    # partial content MSE already carries 1/numel of the WHOLE map: the reduced slot is the level's loss
+                    ops.mse_fwd(tap, sh.target_content_band, 1.0 / sh.content_numel_global, content_slot[li],
+                                sh.wss.for_reduce('content', dev))
             xs[li] = y
 
         lanes.each(active, step)
-    # raw partial Grams + partial content SSE of every level -> ONE all-reduce -> identical finalize on every rank
-    n_packed = sum((sh.n_packed + 3) // 4 * 4 for sh in levels)      # every level's block stays 16-byte aligned
-    packed_all = torch.zeros(n_packed, dtype=torch.float32, device=dev)
-    packs, o = [], 0
-    for sh in levels:
-        packs.append(packed_all[o:o + sh.n_packed])
-        o += (sh.n_packed + 3) // 4 * 4
-
-    def partials(li):
-        sh, packed = levels[li], packs[li]
-        for j, k in enumerate(sh.sidx):
-            f = taps[li][k]
-            c, hw_band = f.shape[1], f.shape[2] * f.shape[3]
-            ops.gram_mse_fwd_nhwc(f, c, hw_band, 1.0, None, packed[sh.offs[j]:sh.offs[j] + c * c], None,
-                                  sh.wss.for_gram(j, c, hw_band, dev))
-        # partial content MSE already carries 1/numel of the WHOLE map: the all-reduced slot is the level's content loss
-        ops.mse_fwd(taps[li][sh.cidx], sh.target_content_band, 1.0 / sh.content_numel_global, packed[sh.content_slot],
-                    sh.wss.for_reduce('content', dev))
-
-    lanes.each(active, partials)
-    with ops.timed(dev, ('allreduce_packed_grams', n_packed)):
-        grp.all_reduce_sum(packed_all)
+        # style taps are produced in slot order: everything up to the end of the last finished tap can be reduced now
+        done_taps = [sidx0.index(k) for k in plan.taps_at.get(sidx, ()) if k in sidx0]
+        if done_taps:
+            j = max(done_taps)
+            hi = tap_off[j + 1] if j + 1 < len(sidx0) else n_packed      # the last tap takes the content block along
+            last = j + 1 == len(sidx0)
+            if hi > reduced_to and (overlap or last):
+                all_reduce_block(reduced_to, hi, last)
+                reduced_to = hi
+    if reduced_to < n_packed:                      # defensive: taps not in ascending slot order
+        all_reduce_block(reduced_to, n_packed, True)
+    for ev in pending:
+        main.wait_event(ev)
     # every rank finalises identically: ALL Grams of ALL levels in one launch (D = G/(C HW) - A rounded to TF32 for the
     # backward's operand, per-layer MSE), then per level TV + the weighted sum
     items, ds_all, vals_all = [], [], []
     for li, sh in enumerate(levels):
-        packed = packs[li]
         n_style = len(sh.sidx)
         vals = torch.empty(n_style + 1, dtype=torch.float32, device=dev)   # style mse[n] | tv
         ds = {}
@@ -340,7 +403,7 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
             st_ = par.LAYER_STRIDE[k]
             hw_global = (sh.H // st_) * (sh.W // st_)
             d = ops.new_d(c, sh.bf16, dev)
-            items.append((packed[sh.offs[j]:sh.offs[j] + c * c], c, 1.0 / (c * hw_global), sh.target_grams[j], d, vals[j],
+            items.append((gram_slot[li][j], c, 1.0 / (c * hw_global), sh.target_grams[j], d, vals[j],
                           ops.d_round_mode(c, sh.bf16)))
             ds[k] = (d, hw_global)
         ds_all.append(ds)
@@ -353,7 +416,7 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
         ops.gram_finalize_batch(items[a:a + ops.L.AST_FINALIZE_MAX_ITEMS], fin_ws[1])
     out4s, per_level = [], []
     for li, sh in enumerate(levels):
-        packed, im, vals = packs[li], imgs[li], vals_all[li]
+        im, vals = imgs[li], vals_all[li]
         cw, sw, tvw = sh.weights
         n_style = len(sh.sidx)
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
@@ -363,14 +426,14 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
             sums2 = torch.empty(2, dtype=torch.float32, device=dev)
             tv_val = vals[n_style]
             ops.tv_fwd(im, sums2, tv_val, sh.wss.for_reduce('tv', dev))
-        ops._launch(dev, ('combine',), 'ast_level_combine', vals.data_ptr(), n_style, packed[sh.content_slot].data_ptr(),
+        ops._launch(dev, ('combine',), 'ast_level_combine', vals.data_ptr(), n_style, content_slot[li].data_ptr(),
                     tv_val.data_ptr(), cw, sw, tvw, out4.data_ptr())
         out4s.append(out4)
         per_level.append((sh, sh.generation, ds_all[li], im, sums2))
     return out4s, per_level
 
 
-def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tensor]:
+def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL, gather=None) -> List[torch.Tensor]:
     """Backward schedule in lock-step: this rank's contribution to every level image's gradient (its band rows,
     plus the TV gradient on rank 0).  g_total: upstream scalar gradient (device tensor) or None."""
     levels = [st[0] for st in state]
@@ -413,8 +476,12 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tenso
         return gp
 
     d_imgs = []
-    for sh, _, _, im, sums2 in state:
-        if grp.rank == 0:                       # TV is replicated: count its gradient once
+    for li, (sh, _, _, im, sums2) in enumerate(state):
+        if gather is not None:
+            # peer-memory gather: this rank's rows go straight into the symmetric gradient buffer; everybody's rows
+            # arrive there with gather.gather(), the (replicated) TV gradient is added afterwards on every rank
+            d = gather.views[li]
+        elif grp.rank == 0:                     # TV is replicated: count its gradient once
             d = torch.empty_like(im)
             ops.tv_bwd(im, sums2, sh.weights[2], gsc, d, False)
         else:
@@ -454,7 +521,7 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tenso
                     gps[li] = gxp
                 else:
                     c0 = gxp.shape[1]
-                    ops.hwc_to_chw(gxp, d_imgs[li], c0, sh.hb * sh.W, True, plane=sh.H * sh.W, x_off=sh.W * c0,
+                    ops.hwc_to_chw(gxp, d_imgs[li], c0, sh.hb * sh.W, gather is None, plane=sh.H * sh.W, x_off=sh.W * c0,
                                    y_off=sh.r0 * sh.W)
                     gps[li] = None
 
@@ -473,4 +540,9 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL) -> List[torch.Tenso
                 gps[li] = gxp
 
             lanes.each(live, pool)
+    if gather is not None:
+        with ops.timed(dev, ('gather_image_grad', len(d_imgs))):
+            gather.gather()                     # every rank's rows of every level, in place
+        for (sh, _, _, im, sums2), d in zip(state, d_imgs):
+            ops.tv_bwd(im, sums2, sh.weights[2], gsc, d, True)
     return d_imgs

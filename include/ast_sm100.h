@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 7
+#define AST_ABI_VERSION 8
 
 #define AST_OK               0
 #define AST_ERR_INVALID     -1   /* bad argument (null pointer, non-positive size, misalignment) */
@@ -191,6 +191,37 @@ typedef struct ast_halo_row {
   int64_t     slot_stride;
 } ast_halo_row;
 int ast_halo_exchange(const ast_halo_row* rows, int n_rows, void* stream);
+
+/* ---- Image-gradient all-gather of a row-band sharded closure through NVLink peer memory ---------------------
+ * (no reference counterpart).  The rows of the gradient pyramid owned by different ranks are disjoint, so instead of
+ * all-reducing the whole image gradient every rank stores ITS rows (segments of a symmetric buffer: same layout on every
+ * rank) into every peer's buffer and waits for theirs — one launch, afterwards all ranks hold identical gradients.
+ *   local_base / peer_base[p] : my symmetric buffer and peer p's, peer-mapped; a segment is [seg_off, seg_off + seg_bytes)
+ *                               of both (at most AST_GATHER_MAX_SEGS = levels x planes row ranges);
+ *   ready_* / arrive_*        : per-peer uint32 sequence counters in symmetric memory (remote = peer p's counter for me,
+ *                               local = my counter for peer p), zero-initialised;
+ *   state                     : 32 zero-initialised uint32 of LOCAL device memory.
+ * ast_band_announce (start of a closure, stream-ordered after the optimizer update that read the previous gradient)
+ * tells every peer that my buffer may be overwritten; ast_band_gather waits for the peers' announcements before it
+ * stores, so one buffer is enough (the gradient keeps its address across CUDA-graph replays).  Both sides must run
+ * the same sequence of announce / gather calls. */
+#define AST_GATHER_MAX_PEERS 7
+#define AST_GATHER_MAX_SEGS  24
+typedef struct ast_band_gather_desc {
+  const char* local_base;
+  char*       peer_base[AST_GATHER_MAX_PEERS];
+  uint32_t*   ready_remote[AST_GATHER_MAX_PEERS];
+  const uint32_t* ready_local[AST_GATHER_MAX_PEERS];
+  uint32_t*   arrive_remote[AST_GATHER_MAX_PEERS];
+  const uint32_t* arrive_local[AST_GATHER_MAX_PEERS];
+  uint32_t*   state;
+  int64_t     seg_off[AST_GATHER_MAX_SEGS];
+  int64_t     seg_bytes[AST_GATHER_MAX_SEGS];
+  int32_t     n_peers;
+  int32_t     n_segs;
+} ast_band_gather_desc;
+int ast_band_announce(const ast_band_gather_desc* desc, void* stream);
+int ast_band_gather(const ast_band_gather_desc* desc, void* stream);
 
 /* ---- Total variation (math_utils.py:37-41) -------------------------------------------------
  *   sums[0] = sum |y[..., :-1] - y[..., 1:]|,  sums[1] = sum |y[:, :-1, :] - y[:, 1:, :]|

@@ -33,6 +33,9 @@ class ThreadGroup:
 
     def all_reduce_sum(self, t):
         sh = self.shared
+        # the product may call this on a side stream (overlapped partial-Gram all-reduce): the emulation reads the other
+        # threads' buffers from THIS thread's stream, so every thread first waits for its own producers on the host
+        torch.cuda.synchronize()
         sh['bufs'][self.rank] = t
         sh['barrier'].wait()
         total = sh['bufs'][0].clone()
@@ -40,6 +43,7 @@ class ThreadGroup:
             total = total + sh['bufs'][r]
         sh['barrier'].wait()
         t.copy_(total)
+        torch.cuda.synchronize()
         sh['barrier'].wait()
 
     def exchange(self, sends, recvs):
