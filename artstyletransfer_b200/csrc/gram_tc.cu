@@ -38,6 +38,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn get_encode_fn() {
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a context current on the calling thread.  A thread whose first CUDA
+  // work is one of our launches (torch's autograd engine thread on device 0, when no allocation preceded it) has none
+  // yet — CUDA_ERROR_INVALID_CONTEXT (201), seen on a B200 in the first backward of a sharded job.  cudaFree(0) binds
+  // the primary context; once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   static EncodeTiledFn fn = nullptr;   // resolved once; pure function of the driver
   if (!fn) {
     void* p = nullptr;

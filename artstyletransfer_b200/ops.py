@@ -175,6 +175,8 @@ def _thread_ws(kind: str, nbytes: int, device: torch.device) -> Workspace:
 def effective_precision(precision: int, ptr: int, C: int, HW: int, ld: int) -> int:
     """TF32 (tcgen05/TMA) when the operand is addressable by TMA, else the exact fp32 CUDA kernels — still this
     library's sm_100a code, never a CPU or torch fallback.  Only toy shapes (HW % 4 != 0) take the second branch."""
+    if precision == L.AST_PREC_BF16:       # BF16 operands exist for the channels-last 512-channel backward only
+        precision = L.AST_PREC_TF32
     if precision == L.AST_PREC_TF32 and not L.load().ast_gram_tf32_supported(ptr, C, HW, ld):
         return L.AST_PREC_FP32
     return precision

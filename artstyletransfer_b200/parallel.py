@@ -57,9 +57,20 @@ class BandPlan:
         return self.r0 // stride, self.r1 // stride
 
 
-# how the halo rows of a lock-step step travel: 'nccl' = one grouped send/recv, 'peer' = one ast_halo_exchange launch
-# over NVLink peer memory (PeerHaloGroup)
-DEFAULT_HALO = 'nccl'
+# how the halo rows of a lock-step step (and, with them, the image gradient) travel: 'peer' = one ast_halo_exchange /
+# ast_band_gather launch over NVLink peer memory (PeerHaloGroup, PeerGradGather; validated between processes at 2 and 8
+# GPUs in round 2: bit-identical losses, 8 % faster at 8 GPUs), 'nccl' = grouped send/recv + all-reduce.  'peer' falls
+# back to 'nccl' — on every rank together — when torch symmetric memory cannot be set up on the box.
+DEFAULT_HALO = 'peer'
+
+
+def all_ranks_ok(ok: bool, device: torch.device) -> bool:
+    """Collective: True only when `ok` holds on every rank (so that all ranks take the same transport)."""
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(int(flag.item()))
+
+
 BAND_OVERHEAD = float(os.environ.get('AST_BAND_OVERHEAD', '0.015'))
 MIN_BAND_ROWS = 2 * ALIGN
 
@@ -584,7 +595,7 @@ def maybe_shard(loss_builders, optimizing_img, neural_net, content_idx, style_id
     When every level can take the halo-exchange path the rows of the WHOLE pyramid are dealt out by PyramidBands
     (level-aware: a rank owns rows of one or two levels, AST_BANDS=uniform restores equal bands of every level);
     otherwise each shardable level is cut into `world` equal bands as before."""
-    global PLAN
+    global PLAN, _GROUP
     PLAN = None
     if _GROUP is None or _GROUP.world == 1 and os.environ.get('AST_SHARD_SINGLE', '0') != '1':
         return 0
@@ -601,7 +612,15 @@ def maybe_shard(loss_builders, optimizing_img, neural_net, content_idx, style_id
     if whole and not (uniform and not all(BandPlan.shardable(lh, world_) for lh, _ in sizes)):
         PLAN = PyramidBands(sizes, world_, uniform=uniform)
         if hasattr(_GROUP, 'prepare'):           # peer-memory halo exchange: symmetric staging for the widest row
-            _GROUP.prepare(optimizing_img.device, 4 * 64 * sizes[0][1])
+            err = None
+            try:
+                _GROUP.prepare(optimizing_img.device, 4 * 64 * sizes[0][1])
+            except Exception as e:               # no symmetric memory on this box
+                err = e
+            if not all_ranks_ok(err is None, optimizing_img.device):
+                import warnings
+                warnings.warn(f'peer-memory halo exchange unavailable ({err!r}); using grouped NCCL send/recv')
+                _GROUP = TorchDistGroup()
         for i, lb in enumerate(loss_builders):
             r0, r1 = PLAN.band(i, rank)
             up, dn = PLAN.neighbours(i, rank)

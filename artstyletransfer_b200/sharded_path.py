@@ -217,8 +217,17 @@ class ShardedPyramid:
         self.gather = None
         grp = levels[0].group
         if isinstance(grp, par.PeerHaloGroup) and grp.world > 1 and os.environ.get('AST_GRAD_GATHER', '1') != '0':
-            self.gather = par.PeerGradGather(grp, levels[0].device, [(sh.H, sh.W) for sh in levels],
-                                             [(sh.r0, sh.r1) for sh in levels])
+            gather = err = None
+            try:
+                gather = par.PeerGradGather(grp, levels[0].device, [(sh.H, sh.W) for sh in levels],
+                                            [(sh.r0, sh.r1) for sh in levels])
+            except Exception as e:                # e.g. more ranks than the kernel's descriptor holds
+                err = e
+            if par.all_ranks_ok(err is None, levels[0].device):
+                self.gather = gather
+            else:
+                import warnings
+                warnings.warn(f'peer-memory gradient gather unavailable ({err!r}); all-reducing the image gradient')
 
     def evaluate(self, optimizing_img: torch.Tensor):
         """image leaf -> summed loss over the levels (neural_style_transfer.py:168-185), differentiable."""
