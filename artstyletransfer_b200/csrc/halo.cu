@@ -16,7 +16,7 @@
 //   tickets    two self-resetting counters find the last CTA of a row: the one that publishes the arrival counter
 //              after every CTA's stores, and the one that advances `count` after every CTA has read it.
 // The CTAs of one launch must be co-resident (they spin on the neighbour, whose progress needs our stores):
-// grid = 8 x n_rows <= 128 CTAs of 512 threads, a fraction of the machine.  A spin that lasts ~4 s traps.
+// grid = (1..32) x n_rows <= 512 CTAs of 512 threads (4 per SM: all resident).  A spin that lasts ~4 s traps.
 #include "ast_common.cuh"
 
 namespace ast {
@@ -25,8 +25,8 @@ struct HaloArgs {
   ast_halo_row rows[AST_HALO_MAX_ROWS];
 };
 
-constexpr int kHaloCtas = 8;
-constexpr int kHaloThreads = 512;
+constexpr int kHaloCtasMax = 32;      // CTAs per row: ~32 KB each (a 786 KB relu1_x row of the 2048x3072 level takes 24);
+constexpr int kHaloThreads = 512;     // 16 rows x 32 CTAs x 512 threads still fit the machine at once (they spin)
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -115,7 +115,11 @@ extern "C" int ast_halo_exchange(const ast_halo_row* rows, int n_rows, void* str
     }
     args.rows[k] = r;
   }
-  halo_exchange_kernel<<<dim3(kHaloCtas, n_rows), kHaloThreads, 0, static_cast<cudaStream_t>(stream)>>>(args);
+  int64_t max_bytes = 0;
+  for (int k = 0; k < n_rows; ++k) max_bytes = rows[k].bytes > max_bytes ? rows[k].bytes : max_bytes;
+  int ctas = (int)((max_bytes + 32767) / 32768);
+  ctas = ctas < 1 ? 1 : (ctas > kHaloCtasMax ? kHaloCtasMax : ctas);
+  halo_exchange_kernel<<<dim3(ctas, n_rows), kHaloThreads, 0, static_cast<cudaStream_t>(stream)>>>(args);
   return check_launch("halo_exchange");
 }
 

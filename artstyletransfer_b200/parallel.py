@@ -321,6 +321,26 @@ class PeerHaloGroup(TorchDistGroup):
         ops._launch(dev, ('halo_exchange', len(rows)), 'ast_halo_exchange', arr, len(rows))
 
 
+def grad_gather_layout(sizes, bands):
+    """Pure host logic of PeerGradGather: byte offsets of the levels' (3, H, W) fp32 gradients in the symmetric buffer
+    (256-byte aligned), the offset of the flag area, and this rank's segments [(offset, bytes)] — one per plane of every
+    level it owns rows [r0, r1) of."""
+    offs, o = [], 0
+    for h, w in sizes:
+        offs.append(o)
+        o += (3 * h * w * 4 + 255) // 256 * 256
+    segs = []
+    for i, ((h, w), (r0, r1)) in enumerate(zip(sizes, bands)):
+        if r1 <= r0:
+            continue
+        for c in range(3):
+            off, nbytes = offs[i] + (c * h + r0) * w * 4, (r1 - r0) * w * 4
+            if off % 16 or nbytes % 16:
+                raise ValueError('gradient rows must be 16-byte aligned (level widths multiples of 4)')
+            segs.append((off, nbytes))
+    return offs, o, segs
+
+
 class PeerGradGather:
     """The image-gradient pyramid of a row-band sharded job in NVLink peer memory (ast_band_gather, csrc/halo.cu).
 
@@ -338,11 +358,9 @@ class PeerGradGather:
         self.rank, self.world = group.rank, group.world
         if self.world - 1 > L.AST_GATHER_MAX_PEERS:
             raise ValueError(f'peer-memory gradient gather supports {L.AST_GATHER_MAX_PEERS + 1} ranks')
-        offs, o = [], 0
-        for h, w in sizes:
-            offs.append(o)
-            o += (3 * h * w * 4 + 255) // 256 * 256
-        flags_off = o
+        offs, flags_off, segs = grad_gather_layout(sizes, bands)
+        if len(segs) > L.AST_GATHER_MAX_SEGS:
+            raise ValueError('too many gradient segments for ast_band_gather')
         total = flags_off + 256 * 2 * self.world
         enable = getattr(symm_mem, 'enable_symm_mem_for_group', None)
         if enable is not None:
@@ -371,19 +389,9 @@ class PeerGradGather:
             d.arrive_local[k] = ptrs[self.rank] + flags_off + 256 * (self.world + r)
         d.state = self._state.data_ptr()
         d.n_peers = len(peers)
-        n = 0
-        for i, ((h, w), (r0, r1)) in enumerate(zip(sizes, bands)):
-            if r1 <= r0:
-                continue
-            for c in range(3):
-                if n >= L.AST_GATHER_MAX_SEGS:
-                    raise ValueError('too many gradient segments for ast_band_gather')
-                d.seg_off[n] = offs[i] + (c * h + r0) * w * 4
-                d.seg_bytes[n] = (r1 - r0) * w * 4
-                if d.seg_off[n] % 16 or d.seg_bytes[n] % 16:
-                    raise ValueError('gradient rows must be 16-byte aligned (level widths multiples of 4)')
-                n += 1
-        d.n_segs = n
+        for n, (off, nbytes) in enumerate(segs):
+            d.seg_off[n], d.seg_bytes[n] = off, nbytes
+        d.n_segs = len(segs)
         self._desc = d
         self._device = device
 

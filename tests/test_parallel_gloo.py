@@ -313,3 +313,25 @@ def test_peer_halo_group_pairs_slots_and_counters(monkeypatch):
     assert len(rows) == 16 and calls == 1
     with pytest.raises(ValueError, match='exceeds the staging slot'):
         rows_of(1, [(torch.zeros(4, 64, 32), 0, 2, 0)], False)
+
+
+@pytest.mark.parametrize('world', [2, 3, 4, 8])
+def test_grad_gather_segments_tile_the_gradient_pyramid(world):
+    """PeerGradGather's host logic: over all ranks, the segments every rank pushes into its peers' symmetric buffers
+    cover every byte of every level's (3, H, W) gradient exactly once (disjoint rows -> a gather, not a reduction)."""
+    import numpy as np
+    from artstyletransfer_b200 import parallel
+    sizes = [(2048 >> i, 3072 >> i) for i in range(4)]
+    plan = parallel.PyramidBands(sizes, world)
+    offs, flags_off, _ = parallel.grad_gather_layout(sizes, [(0, 0)] * 4)
+    cover = np.zeros(flags_off // 16, dtype=np.int32)
+    for rank in range(world):
+        _, _, segs = parallel.grad_gather_layout(sizes, [plan.band(i, rank) for i in range(4)])
+        assert len(segs) <= 24
+        for off, nbytes in segs:
+            assert off % 16 == 0 and nbytes % 16 == 0
+            cover[off // 16:(off + nbytes) // 16] += 1
+    for i, (h, w) in enumerate(sizes):
+        lvl = cover[offs[i] // 16:(offs[i] + 3 * h * w * 4) // 16]
+        assert lvl.min() == 1 and lvl.max() == 1
+    assert cover.sum() == sum(3 * h * w * 4 for h, w in sizes) // 16
