@@ -535,6 +535,9 @@ def run_ours(args):
         'per_rank_busy_ms_eager_pass': per_rank_busy,
         'setup_kernels': kernel_table(setup_kernels, pk)[:8],
         'init_image_s': round(init_s, 4), 'loss_after': loss_now, 'parity': parity,
+        # `value` counts reference iterations (closures: what iters_num counts); LBFGS takes two per optimizer.step
+        'closures_per_s': round(value, 4),
+        'optimizer_steps_per_s': round(value / (2 if args.optimizer == 'lbfgs' else 1), 4),
     }
     if world == 1 and not args.no_library_baseline:
         line['library_baseline'] = library_baseline(args, dev, content_levels, style_levels, init)
