@@ -73,6 +73,10 @@ def all_ranks_ok(ok: bool, device: torch.device) -> bool:
 
 BAND_OVERHEAD = float(os.environ.get('AST_BAND_OVERHEAD', '0.015'))
 MIN_BAND_ROWS = 2 * ALIGN
+# Halo rows a band swaps per exchange on the channels-last path (halo_schedule): 2 = every second convolution runs on
+# redundantly computed edge rows instead of waiting for the neighbours (13 synchronisation points per closure instead
+# of 25, for 2 extra convolution rows per band and layer); 1 = an exchange before every convolution (round 1).
+HALO_DEPTH = int(os.environ.get('AST_HALO_DEPTH', '2'))
 
 
 class PyramidBands:
@@ -193,6 +197,13 @@ class PyramidBands:
         dn = next((r for r in range(rank + 1, self.world) if edges[r + 1] > edges[r]), None)
         return up, dn
 
+    def halo_depth(self, wanted: Optional[int] = None) -> int:
+        """Rows of halo every band can swap per exchange: `wanted` (default HALO_DEPTH) when every band owns at least
+        that many rows at the deepest layer of the feature path (stride ALIGN), else 1.  The same on every rank."""
+        wanted = HALO_DEPTH if wanted is None else int(wanted)
+        rows = [e[r + 1] - e[r] for e in self.bounds for r in range(self.world) if e[r + 1] > e[r]]
+        return wanted if wanted <= 1 or min(rows) // ALIGN >= wanted else 1
+
     def describe(self) -> str:
         parts = []
         for li, ((h, w), edges) in enumerate(zip(self.sizes, self.bounds)):
@@ -277,7 +288,7 @@ class PeerHaloGroup(TorchDistGroup):
             raise ValueError(f'peer halo exchange supports {self.MAX_LEVELS} pyramid levels; got level {level}')
         return 2 * level + direction
 
-    def exchange_rows(self, entries, zero_border: bool) -> None:
+    def exchange_rows(self, entries, zero_border: bool, depth: int = 1) -> None:
         from . import _lib as L, ops
         if self._hdl is None:
             raise RuntimeError('PeerHaloGroup.prepare() has not run (parallel.maybe_shard calls it)')
@@ -300,18 +311,22 @@ class PeerHaloGroup(TorchDistGroup):
             rows.append(r)
 
         dev = None
+        d = int(depth)
         for r, up, dn, level in entries:
             dev = r.device
-            h = r.shape[0] - 2
-            # my "from above" entry (direction 0) pairs with the upper neighbour's "from below" entry (1)
+            h = r.shape[0] - 2 * d
+            if h < d:
+                raise ValueError(f'a band of {h} rows cannot hand {d} rows to its neighbours')
+            # my "from above" entry (direction 0) pairs with the upper neighbour's "from below" entry (1); the `d` edge
+            # rows are one contiguous piece
             if up is not None:
-                add(r[1], r[0], up, self._entry(level, 0), self._entry(level, 1))
+                add(r[d:2 * d], r[0:d], up, self._entry(level, 0), self._entry(level, 1))
             elif zero_border:
-                add(None, r[0], None, 0, 0)
+                add(None, r[0:d], None, 0, 0)
             if dn is not None:
-                add(r[h], r[h + 1], dn, self._entry(level, 1), self._entry(level, 0))
+                add(r[h:h + d], r[h + d:h + 2 * d], dn, self._entry(level, 1), self._entry(level, 0))
             elif zero_border:
-                add(None, r[h + 1], None, 0, 0)
+                add(None, r[h + d:h + 2 * d], None, 0, 0)
         if not rows:
             return
         if len(rows) > L.AST_HALO_MAX_ROWS:
@@ -404,9 +419,53 @@ class PeerGradGather:
         ops._launch(self._device, ('band_gather', self._desc.n_segs), 'ast_band_gather', self._desc)
 
 
-def halo_exchange(group, rows, zero_border: bool = False) -> None:
-    """rows: one (h + 2, w, C) contiguous view of a padded band, or a list of them (row 0 and row h+1 are the
-    halos); a list entry may also be (view, up, dn[, level]) naming the ranks that own the rows above / below this
+def halo_schedule(kinds: Sequence[str], taps_at, depth: int):
+    """Pure host logic: WHERE the lock-step feature path swaps halo rows when a band carries `depth` halo rows.
+
+    kinds: 'conv' / 'pool' per step of the feature path; taps_at: the steps that have a loss tap; depth: 1 or 2.
+    A 3x3 convolution over a band whose `v` innermost halo rows per side are valid leaves v - 1 valid halo rows
+    (the band's outer output rows saw its zero padding instead of real rows), a 2x2 max-pool of the owned rows
+    leaves none; the image band itself comes from the replicated image with all `depth` rows.  An exchange restores
+    `depth`.  So with depth 2 only every second convolution of a block needs its neighbours — 6 forward exchanges
+    for VGG19 up to conv5_1 instead of 12.  The backward is the mirror image on the gradient w.r.t. each
+    convolution's output: backward-data over a band with u valid gradient halo rows leaves u - 1; the steps that run
+    without an exchange apply their loss-tap gradients and ReLU masks on the owned rows +- 1 (`ext`), reading the
+    forward band's halo row, which is valid there because that band fed a convolution.  7 instead of 13.
+
+    Returns (forward: set of steps with an exchange BEFORE them, backward: {conv step: ('exchange', 0) |
+    ('local', ext)} for every convolution at or below the deepest tap)."""
+    depth = int(depth)
+    if depth not in (1, 2):
+        raise ValueError(f'halo depth {depth}: 1 or 2 rows')
+    fwd, v = set(), depth
+    for s, kind in enumerate(kinds):
+        if kind == 'conv':
+            if v < 1:
+                fwd.add(s)
+                v = depth
+            v -= 1
+        else:
+            v = 0
+    bwd, u, flowing = {}, 0, False
+    for s in range(len(kinds) - 1, -1, -1):
+        if not (flowing or s in taps_at):
+            continue
+        flowing = True
+        if kinds[s] == 'conv':
+            if u < 1:
+                bwd[s] = ('exchange', 0)
+                u = depth
+            else:
+                bwd[s] = ('local', u)
+            u -= 1
+        else:
+            u = 0
+    return fwd, bwd
+
+
+def halo_exchange(group, rows, zero_border: bool = False, depth: int = 1) -> None:
+    """rows: one (h + 2 depth, w, C) contiguous view of a padded band, or a list of them (the first and last `depth`
+    rows are the halos; depth rows are contiguous in NHWC, so they travel as one piece); a list entry may also be (view, up, dn[, level]) naming the ranks that own the rows above / below this
     band (None at the image border) — the default is rank - 1 / rank + 1, the plan of equal bands — and the index
     of the pyramid level (only the peer-memory group needs it: one staging slot pair per level and direction).  Sends the first /
     last owned row of every band to its neighbours and receives their edge rows into the halos, all in ONE grouped
@@ -427,22 +486,25 @@ def halo_exchange(group, rows, zero_border: bool = False) -> None:
                             group.rank + 1 if group.rank + 1 < group.world else None, n))
         else:
             entries.append(tuple(entry) if len(entry) == 4 else (*entry, n))
+    d = int(depth)
     if hasattr(group, 'exchange_rows'):          # one peer-memory kernel for the whole step (PeerHaloGroup)
-        group.exchange_rows(entries, zero_border)
+        group.exchange_rows(entries, zero_border, d)
         return
     sends, recvs = [], []
     for r, up, dn, _ in entries:
-        h = r.shape[0] - 2
+        h = r.shape[0] - 2 * d
+        if h < d:
+            raise ValueError(f'a band of {h} rows cannot hand {d} rows to its neighbours')
         if up is not None:
-            sends.append((r[1], up))
-            recvs.append((r[0], up))
+            sends.append((r[d:2 * d] if d > 1 else r[1], up))
+            recvs.append((r[0:d] if d > 1 else r[0], up))
         elif zero_border:
-            r[0].zero_()
+            r[0:d].zero_()
         if dn is not None:
-            sends.append((r[h], dn))
-            recvs.append((r[h + 1], dn))
+            sends.append((r[h:h + d] if d > 1 else r[h], dn))
+            recvs.append((r[h + d:h + 2 * d] if d > 1 else r[h + 1], dn))
         elif zero_border:
-            r[h + 1].zero_()
+            r[h + d:].zero_()
     group.exchange(sends, recvs)
 
 
@@ -462,7 +524,9 @@ def init_sharding(group=None) -> None:
     if group is None:
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError('init_sharding() needs an initialized torch.distributed process group')
-        group = PeerHaloGroup() if os.environ.get('AST_HALO', DEFAULT_HALO) == 'peer' else TorchDistGroup()
+        # peer memory needs CUDA ranks of one node: any other backend (the gloo host-logic tests) uses send/recv
+        peer = os.environ.get('AST_HALO', DEFAULT_HALO) == 'peer' and 'nccl' in str(dist.get_backend()).lower()
+        group = PeerHaloGroup() if peer else TorchDistGroup()
     _GROUP = group
 
 
@@ -619,10 +683,11 @@ def maybe_shard(loss_builders, optimizing_img, neural_net, content_idx, style_id
         for i, (lh, lw) in enumerate(sizes))
     if whole and not (uniform and not all(BandPlan.shardable(lh, world_) for lh, _ in sizes)):
         PLAN = PyramidBands(sizes, world_, uniform=uniform)
+        depth = PLAN.halo_depth()
         if hasattr(_GROUP, 'prepare'):           # peer-memory halo exchange: symmetric staging for the widest row
             err = None
             try:
-                _GROUP.prepare(optimizing_img.device, 4 * 64 * sizes[0][1])
+                _GROUP.prepare(optimizing_img.device, depth * 4 * 64 * sizes[0][1])
             except Exception as e:               # no symmetric memory on this box
                 err = e
             if not all_ranks_ok(err is None, optimizing_img.device):
@@ -633,7 +698,8 @@ def maybe_shard(loss_builders, optimizing_img, neural_net, content_idx, style_id
             r0, r1 = PLAN.band(i, rank)
             up, dn = PLAN.neighbours(i, rank)
             lb.shard = ShardedPathLevel(_GROUP, plans[i], lb.target_images[0], lb.target_images[1], content_idx,
-                                        style_idx, weights, sizes[i][0], sizes[i][1], band=(r0, r1, up, dn))
+                                        style_idx, weights, sizes[i][0], sizes[i][1], band=(r0, r1, up, dn),
+                                        halo_depth=depth)
         return len(loss_builders)
     n = 0
     for i, lb in enumerate(loss_builders):

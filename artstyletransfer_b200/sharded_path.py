@@ -91,10 +91,14 @@ class ShardedPathLevel:
     """Replaces LossBuilder.build for one level when sharding is on (same return contract)."""
 
     def __init__(self, group, plan: fp.FeaturePlan, content_img: torch.Tensor, style_img: torch.Tensor,
-                 content_idx: int, style_idx: Sequence[int], weights, height: int, width: int, band=None):
+                 content_idx: int, style_idx: Sequence[int], weights, height: int, width: int, band=None,
+                 halo_depth: int = None):
         """band: (r0, r1, up, dn) from parallel.PyramidBands — the owned rows and the ranks holding the rows above /
         below (None at the image border); r0 == r1 when this rank does not work on the level (it still joins the
-        all-reduce and finalises the loss).  Default: `world` equal bands, neighbours rank -+ 1."""
+        all-reduce and finalises the loss).  Default: `world` equal bands, neighbours rank -+ 1.
+        halo_depth: halo rows per side of every band (parallel.halo_schedule; the SAME on every rank and level of a
+        lock-step pyramid: PyramidBands.halo_depth()).  Default: parallel.HALO_DEPTH for equal bands that are tall
+        enough, 1 for an explicit band."""
         self.group, self.plan = group, plan
         self.cidx, self.sidx = content_idx, list(style_idx)
         self.weights = tuple(float(w) for w in weights)
@@ -103,8 +107,16 @@ class ShardedPathLevel:
             bp = par.BandPlan(height, group.rank, group.world, halo=0)
             band = (bp.r0, bp.r1, group.rank - 1 if group.rank > 0 else None,
                     group.rank + 1 if group.rank + 1 < group.world else None)
+            if halo_depth is None:
+                halo_depth = par.HALO_DEPTH if (height // group.world) // par.ALIGN >= par.HALO_DEPTH else 1
+        self.D = 1 if halo_depth is None or not FUSED_BAND_CONV else int(halo_depth)
+        if self.D not in (1, 2):
+            raise ValueError(f'halo depth {self.D}: 1 or 2 rows')
         self.r0, self.r1, self.up, self.dn = band
         self.hb = self.r1 - self.r0
+        if self.hb and self.hb // par.ALIGN < self.D:
+            raise ValueError(f'a band of {self.hb} rows cannot hand {self.D} halo rows to its neighbours at stride '
+                             f'{par.ALIGN}')
         from . import neural_style_transfer as _nst
         self.bf16 = ops._prec(_nst.PRECISION) == ops.L.AST_PREC_BF16
         if self.hb and (self.r0 % par.ALIGN or self.r1 % par.ALIGN or not 0 <= self.r0 < self.r1 <= height):
@@ -117,6 +129,14 @@ class ShardedPathLevel:
         cs = par.LAYER_STRIDE[content_idx]
         crow = _rows(tg.content_cl)
         self.target_content_band = crow[self.r0 // cs:self.r1 // cs].contiguous()
+        # the same band with one more row per side (zeros outside the image): the target under a content tap whose
+        # gradient is applied on the owned rows +- 1 (a backward step that runs without an exchange)
+        self._target_content_ext = None
+        if self.hb:
+            ext = torch.zeros((self.hb // cs + 2, *crow.shape[1:]), dtype=crow.dtype, device=crow.device)
+            lo, hi = max(self.r0 // cs - 1, 0), min(self.r1 // cs + 1, crow.shape[0])
+            ext[lo - (self.r0 // cs - 1):lo - (self.r0 // cs - 1) + hi - lo] = crow[lo:hi]
+            self._target_content_ext = ext
         self.content_numel_global = tg.content_cl.numel()
         self.channels = [g.shape[-1] for g in tg.grams]
         self.offs, self.content_slot, self.n_packed = par.pack_layout(self.channels)
@@ -128,7 +148,8 @@ class ShardedPathLevel:
             return
         # persistent padded activation bands: xin (the image band) and one per step
         c0 = plan.steps[0][3]
-        self.xin = torch.empty((1, c0, self.hb + 2, width), dtype=torch.float32, device=dev, memory_format=_CL).zero_()
+        self.xin = torch.empty((1, c0, self.hb + 2 * self.D, width), dtype=torch.float32, device=dev,
+                               memory_format=_CL).zero_()
         c, h, w = c0, self.hb, width
         for sidx in range(plan.n_steps_needed):
             st = plan.steps[sidx]
@@ -139,15 +160,20 @@ class ShardedPathLevel:
             if st[0] == 'conv' and FUSED_BAND_CONV:
                 self.bufs.append(None)            # the fused convolution allocates its padded output every closure
             else:
-                self.bufs.append(torch.empty((1, c, h + 2, w), dtype=torch.float32, device=dev,
+                self.bufs.append(torch.empty((1, c, h + 2 * self.D, w), dtype=torch.float32, device=dev,
                                              memory_format=_CL).zero_())
+
+    def content_target(self, ext: int) -> torch.Tensor:
+        """Content target rows under the owned rows +- ext (ext 0 or 1) of the tapped layer."""
+        return self.target_content_band if ext == 0 else self._target_content_ext
 
     def build(self, level_img: torch.Tensor):
         return ShardPathFn.apply(self, level_img)
 
 
-def _interior(buf: torch.Tensor) -> torch.Tensor:
-    return buf[:, :, 1:-1, :]
+def _interior(buf: torch.Tensor, depth: int = 1, ext: int = 0) -> torch.Tensor:
+    """The owned rows (+- ext) of a band padded with `depth` halo rows per side."""
+    return buf[:, :, depth - ext:buf.shape[2] - depth + ext, :]
 
 
 def _conv_fwd_into(x_pad, w, out):
@@ -210,6 +236,8 @@ class ShardedPyramid:
 
     def __init__(self, levels: List[ShardedPathLevel]):
         self.levels = list(levels)
+        if len({sh.D for sh in levels}) != 1:
+            raise ValueError('lock-step levels must carry the same halo depth')
         self.lanes = Lanes(levels[0].device, len(levels)) if MULTI_STREAM else _SERIAL
         self.comm = torch.cuda.Stream(levels[0].device)          # the partial-Gram all-reduces (pyramid_forward)
         # image gradient: an all-gather of the ranks' disjoint rows through NVLink peer memory instead of an all-reduce
@@ -294,11 +322,16 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
         sh.generation += 1
         if not sh.hb:
             continue
-        # image band + one row above / below straight from the replicated image (rows outside the image stay 0)
-        lo, hi = max(sh.r0 - 1, 0), min(sh.r1 + 1, sh.H)
+        if sh.D != sh0.D:
+            raise ValueError('lock-step levels must carry the same halo depth')
+        # image band + D rows above / below straight from the replicated image (rows outside the image stay 0)
+        lo, hi = max(sh.r0 - sh.D, 0), min(sh.r1 + sh.D, sh.H)
         c0 = im.shape[1]
         ops.chw_to_hwc(im, sh.xin, c0, (hi - lo) * sh.W, plane=sh.H * sh.W, x_off=lo * sh.W,
-                       y_off=(lo - (sh.r0 - 1)) * sh.W * c0)
+                       y_off=(lo - (sh.r0 - sh.D)) * sh.W * c0)
+    D = sh0.D
+    inner = lambda buf: _interior(buf, D)
+    exchange_before, _ = par.halo_schedule([st[0] for st in plan.steps[:plan.n_steps_needed]], plan.taps_at, D)
     active = [li for li, sh in enumerate(levels) if sh.hb]       # the levels this rank owns rows of
     xs = [sh.xin for sh in levels]
     taps = [[None] * len(plan.tap_step) for _ in levels]
@@ -351,9 +384,9 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
     reduced_to = 0                                 # packed_all[:reduced_to] has been handed to an all-reduce
     for sidx in range(plan.n_steps_needed):
         st = plan.steps[sidx]
-        if st[0] == 'conv' and sidx > 0:
+        if sidx in exchange_before:
             with ops.timed(dev, ('halo_exchange_fwd', len(active), sidx)):
-                par.halo_exchange(grp, [(_rows(xs[li]), levels[li].up, levels[li].dn, li) for li in active])
+                par.halo_exchange(grp, [(_rows(xs[li]), levels[li].up, levels[li].dn, li) for li in active], depth=D)
         feeds_conv = sidx + 1 < plan.n_steps_needed and plan.steps[sidx + 1][0] == 'conv'
 
         def step(li, st=st, sidx=sidx, feeds_conv=feeds_conv):
@@ -364,17 +397,17 @@ def pyramid_forward(levels: Sequence[ShardedPathLevel], imgs: Sequence[torch.Ten
                 if feeds_conv:                      # border halos are the next convolution's zero padding
                     rows = _rows(y)
                     if sh.up is None:
-                        rows[0].zero_()
+                        rows[:D].zero_()
                     if sh.dn is None:
-                        rows[-1].zero_()
+                        rows[-D:].zero_()
             elif st[0] == 'conv':
-                yi = _interior(y)
+                yi = inner(y)
                 _conv_fwd_into(x, st[1], yi)
                 ops.bias_relu_(yi, st[2])
             else:
-                ops.maxpool2x2(_interior(x), _interior(y))
+                ops.maxpool2x2(inner(x), inner(y))
             for k in plan.taps_at.get(sidx, ()):
-                tap = taps[li][k] = _interior(y)
+                tap = taps[li][k] = inner(y)
                 if k in sh.sidx:                    # this band's partial Gram of the tap, straight into its slot
                     j = sh.sidx.index(k)
                     c, hw_band = tap.shape[1], tap.shape[2] * tap.shape[3]
@@ -455,19 +488,25 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL, gather=None) -> Lis
             raise RuntimeError('sharded level: backward() after a newer forward() of the same level — its activation '
                                'bands are persistent buffers; run forward and backward of a closure back to back')
 
-    def new_grad_band(like_interior):
-        """Padded gradient band (1, C, h+2, w) for a tensor shaped like an activation band's interior."""
-        _, c, h, w = like_interior.shape
-        return torch.empty((1, c, h + 2, w), dtype=torch.float32, device=dev, memory_format=_CL)
+    D = sh0.D
+    inner = lambda buf, ext=0: _interior(buf, D, ext)
+    _, schedule = par.halo_schedule([st[0] for st in plan.steps[:plan.n_steps_needed]], plan.taps_at, D)
 
-    def tap_grad(li, k, tap, gp, relu_mask):
+    def new_grad_band(like):
+        """Padded gradient band for a padded activation band of the same shape."""
+        return torch.empty(like.shape, dtype=torch.float32, device=dev, memory_format=_CL)
+
+    def tap_grad(li, k, buf, gp, relu_mask, ext=0):
+        """Gradient of tap k (the owned rows +- ext of the padded activation band `buf`) into the gradient band."""
         sh, _, ds, _, _ = state[li]
         cw, sw, tvw = sh.weights
         n = len(sh.sidx)
         acc = gp is not None
         if not acc:
-            gp = new_grad_band(tap)
-        g = _interior(gp)
+            if ext:
+                raise RuntimeError('the first tap gradient of a band has no valid halo rows to extend into')
+            gp = new_grad_band(buf)
+        tap, g = inner(buf, ext), inner(gp, ext)
         c, hw_band = tap.shape[1], tap.shape[2] * tap.shape[3]
         style, content = k in ds, k == sh.cidx
         fuse_gram = relu_mask and not content and c <= fp.FUSED_TAP_RELU_MAX_C
@@ -476,7 +515,7 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL, gather=None) -> Lis
             ops.gram_bwd_nhwc_auto(d, tap, c, hw_band, (sw / n) * 4.0 / (float(c) * c * c * hw_global), gsc, g, acc,
                                    relu_mask=fuse_gram)
         if content:
-            ops.mse_bwd(tap, sh.target_content_band, cw * 2.0 / sh.content_numel_global, gsc, g, acc or style,
+            ops.mse_bwd(tap, sh.content_target(ext), cw * 2.0 / sh.content_numel_global, gsc, g, acc or style,
                         relu_mask)
         elif not style and not acc:
             g.zero_()
@@ -507,20 +546,26 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL, gather=None) -> Lis
         flowing = True
         live = [li for li in range(len(levels)) if levels[li].hb]
         if st[0] == 'conv':
-            def pre(li, sidx=sidx):              # tap gradients into the band + the ReLU's backward (fused or in place)
+            how, ext = schedule[sidx]
+
+            def pre(li, sidx=sidx, ext=ext):     # tap gradients into the band + the ReLU's backward (fused or in place)
+                # ext = 1 (a step without an exchange): on the owned rows +- 1 — the gradient band is valid there
+                # after the previous backward-data, and so is the forward band (it fed a convolution); rows outside
+                # the image hold activation 0, so the mask zeroes their gradient
                 taps_here = plan.taps_at.get(sidx, ())
                 for n, k in enumerate(taps_here):
                     fuse = n == len(taps_here) - 1 and not masked[li]
-                    gps[li] = tap_grad(li, k, _interior(levels[li].bufs[sidx]), gps[li], fuse)
+                    gps[li] = tap_grad(li, k, levels[li].bufs[sidx], gps[li], fuse, ext)
                     masked[li] = masked[li] or fuse
                 if not masked[li]:
-                    ops.relu_bwd_(_interior(gps[li]), _interior(levels[li].bufs[sidx]))
+                    ops.relu_bwd_(inner(gps[li], ext), inner(levels[li].bufs[sidx], ext))
                 masked[li] = False
 
             lanes.each(live, pre)
-            with ops.timed(dev, ('halo_exchange_bwd', len(live), sidx)):
-                par.halo_exchange(grp, [(_rows(gps[li]), levels[li].up, levels[li].dn, li) for li in live],
-                                  zero_border=True)
+            if how == 'exchange':
+                with ops.timed(dev, ('halo_exchange_bwd', len(live), sidx)):
+                    par.halo_exchange(grp, [(_rows(gps[li]), levels[li].up, levels[li].dn, li) for li in live],
+                                      zero_border=True, depth=D)
 
             def dgrad(li, st=st, sidx=sidx):
                 sh = levels[li]
@@ -530,8 +575,8 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL, gather=None) -> Lis
                     gps[li] = gxp
                 else:
                     c0 = gxp.shape[1]
-                    ops.hwc_to_chw(gxp, d_imgs[li], c0, sh.hb * sh.W, gather is None, plane=sh.H * sh.W, x_off=sh.W * c0,
-                                   y_off=sh.r0 * sh.W)
+                    ops.hwc_to_chw(gxp, d_imgs[li], c0, sh.hb * sh.W, gather is None, plane=sh.H * sh.W,
+                                   x_off=D * sh.W * c0, y_off=sh.r0 * sh.W)
                     gps[li] = None
 
             lanes.each(live, dgrad)
@@ -541,10 +586,10 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL, gather=None) -> Lis
             def pool(li, sidx=sidx, fuse=fuse):
                 sh = levels[li]
                 for k in plan.taps_at.get(sidx, ()):
-                    gps[li] = tap_grad(li, k, _interior(sh.bufs[sidx]), gps[li], False)
-                xi = _interior(sh.bufs[sidx - 1] if sidx > 0 else sh.xin)
-                gxp = new_grad_band(xi)
-                ops.maxpool2x2_bwd(_interior(gps[li]), xi, _interior(gxp), fuse)
+                    gps[li] = tap_grad(li, k, sh.bufs[sidx], gps[li], False)
+                xb = sh.bufs[sidx - 1] if sidx > 0 else sh.xin
+                gxp = new_grad_band(xb)
+                ops.maxpool2x2_bwd(inner(gps[li]), inner(xb), inner(gxp), fuse)
                 masked[li] = fuse
                 gps[li] = gxp
 

@@ -187,7 +187,7 @@ def test_halo_exchange_level_matches_unsharded(seeded_vgg, world, H, W):
         assert float(gr[:, :, hi:].abs().max() if hi < H else 0.0) == 0.0
 
 
-def run_lockstep(world, bands, n_levels, weights=WEIGHTS, content_idx=None, hw=None):
+def run_lockstep(world, bands, n_levels, weights=WEIGHTS, content_idx=None, hw=None, halo_depth=None):
     """The unsharded closure (bicubic chain + every level + backward) and the same closure on `world` emulated ranks
     in lock-step.  Returns a dict: ref_total, ref_grad, totals (per rank), grads (per rank), plan, inputs."""
     from artstyletransfer_b200 import math_utils, neural_style_transfer as nst, ops
@@ -216,6 +216,8 @@ def run_lockstep(world, bands, n_levels, weights=WEIGHTS, content_idx=None, hw=N
     plan = lbs[0].path_plan(img)
     sizes = [(H >> i, W >> i) for i in range(n_levels)]
     pb = PyramidBands(sizes, world, uniform=bands == 'uniform')
+    depth = pb.halo_depth(halo_depth)              # halo rows per exchange (parallel.halo_schedule)
+    assert halo_depth is None or depth == halo_depth
 
     shared = {'bufs': [None] * world, 'barrier': threading.Barrier(world, timeout=60), 'mail': {}}
     results = [None] * world
@@ -229,7 +231,8 @@ def run_lockstep(world, bands, n_levels, weights=WEIGHTS, content_idx=None, hw=N
             torch.cuda.set_device(dev())
             grp = ThreadGroup(rank, world, shared)
             levels = [ShardedPathLevel(grp, plan, c_img[i], s_img[i], cidx, sidx, weights, *sizes[i],
-                                       band=(*pb.band(i, rank), *pb.neighbours(i, rank))) for i in range(n_levels)]
+                                       band=(*pb.band(i, rank), *pb.neighbours(i, rank)), halo_depth=depth)
+                      for i in range(n_levels)]
             pyr = ShardedPyramid(levels)
             out = []
             for _ in range(2):                      # persistent buffers: a second closure must agree bit for bit
@@ -321,8 +324,9 @@ def summarise(tag, run, world):
 
 
 @pytest.mark.timeout(300)
+@pytest.mark.parametrize('depth', [2, 1])
 @pytest.mark.parametrize('world,bands,n_levels', LOCKSTEP_CASES)
-def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, correctly_rounded_convs, world, bands, n_levels):
+def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, correctly_rounded_convs, world, bands, n_levels, depth):
     """The pyramid levels evaluated in lock-step with grouped halo exchanges == the unsharded closure (bicubic chain
     + every level + backward), summed over the emulated ranks.  'uniform': every level cut into `world` equal bands;
     'pyramid': the level-aware plan (parallel.PyramidBands) — unequal bands, ranks that own rows of two levels, ranks
@@ -332,24 +336,28 @@ def test_lockstep_pyramid_matches_unsharded_closure(seeded_vgg, correctly_rounde
     summation orders: the Gram is a sum over positions whose split-K order differs between one 148-CTA launch and
     per-band launches + all-reduce (1e-7 of G), D = G - A amplifies that by |G|/|D| ~ 1e2 and is then rounded to TF32
     for the backward's operand — a bounded, band-edge-free 1e-5-level effect.  Asserted: loss 1e-5, gradient 1e-4."""
-    run = run_lockstep(world, bands, n_levels)
+    run = run_lockstep(world, bands, n_levels, halo_depth=depth)
     pb = run['plan']
     if bands == 'pyramid' and world > 2:           # the plan really is heterogeneous at these sizes
         assert any(pb.band(li, r)[0] == pb.band(li, r)[1] for li in range(n_levels) for r in range(world))
-    lerr, gerr = summarise(f'lockstep[{world}-{bands}-{n_levels}]', run, world)
+    lerr, gerr = summarise(f'lockstep[{world}-{bands}-{n_levels}-depth{depth}]', run, world)
     assert lerr <= 1e-5, lerr
     assert gerr <= 1e-4, gerr
 
 
 @pytest.mark.timeout(300)
+@pytest.mark.parametrize('content_idx,depth', [(5, 2), (5, 1), (3, 2)])
 @pytest.mark.parametrize('world,bands,n_levels', [(2, 'pyramid', 3), (4, 'pyramid', 3), (4, 'uniform', 2)])
-def test_lockstep_pyramid_is_exact_without_gram_noise(seeded_vgg, correctly_rounded_convs, world, bands, n_levels):
+def test_lockstep_pyramid_is_exact_without_gram_noise(seeded_vgg, correctly_rounded_convs, world, bands, n_levels,
+                                                      content_idx, depth):
     """Style weight 0 and the content term moved to the deepest tap (relu5_1): the gradient then flows through every
     convolution, pool, halo exchange and the bicubic chain but through no TF32 Gram, so with correctly rounded
-    convolutions the sharded closure must reproduce the unsharded one to fp32 summation order."""
+    convolutions the sharded closure must reproduce the unsharded one to fp32 summation order.  With two halo rows
+    per exchange (depth 2) every second convolution runs on redundantly computed edge rows; content_idx 3 (relu4_1)
+    puts the content tap on a backward step that runs WITHOUT an exchange, i.e. on the owned rows +- 1."""
     weights = (1e3, 0.0, 1e2)
-    run = run_lockstep(world, bands, n_levels, weights=weights, content_idx=5)
-    lerr, gerr = summarise(f'exact[{world}-{bands}-{n_levels}]', run, world)
+    run = run_lockstep(world, bands, n_levels, weights=weights, content_idx=content_idx, halo_depth=depth)
+    lerr, gerr = summarise(f'exact[{world}-{bands}-{n_levels}-tap{content_idx}-depth{depth}]', run, world)
     assert lerr <= 2e-6, lerr
     assert gerr < 2e-5, gerr
 

@@ -172,6 +172,104 @@ def test_halo_exchange_reproduces_full_convolutions_over_gloo(world):
         assert fwd_err < 1e-10 and bwd_err < 1e-10, (rank, fwd_err, bwd_err)
 
 
+def _halo2_worker(rank, world, port, out):
+    """Two halo rows per exchange (parallel.halo_schedule, depth 2): ONE exchange serves two stacked convolutions, in
+    the forward and in the backward — the scheme of sharded_path.pyramid_forward / pyramid_backward in fp64."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import torch.nn.functional as F
+        from artstyletransfer_b200 import parallel
+        torch.set_num_threads(2)
+        parallel.init_sharding()
+        grp = parallel._GROUP
+        H, W, C1, C2, D = 24, 10, 4, 6, 2
+        r0, r1 = rank * (H // world), (rank + 1) * (H // world)
+        hb = r1 - r0
+        top, bottom = rank == 0, rank == world - 1
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn((1, C1, H, W), generator=g, dtype=torch.float64)
+        w1 = torch.randn((C2, C1, 3, 3), generator=g, dtype=torch.float64)
+        w2 = torch.randn((C1, C2, 3, 3), generator=g, dtype=torch.float64)
+        gout = torch.randn((1, C1, H, W), generator=g, dtype=torch.float64)
+        xr = x.clone().requires_grad_(True)
+        yr = F.conv2d(F.conv2d(xr, w1, padding=1), w2, padding=1)
+        (gref,) = torch.autograd.grad(yr, xr, gout)
+
+        def whole_band_conv(rows, wgt):            # (hb + 4, W, Cin) -> (hb + 4, W, Cout), symmetric zero padding
+            return F.conv2d(rows.permute(2, 0, 1)[None], wgt, padding=1)[0].permute(1, 2, 0).contiguous()
+
+        def whole_band_bwd(grows, wgt, cin):
+            xin = torch.zeros((1, cin, hb + 2 * D, W), dtype=torch.float64, requires_grad=True)
+            (gx,) = torch.autograd.grad(F.conv2d(xin, wgt, padding=1), xin, grows.permute(2, 0, 1)[None])
+            return gx[0].permute(1, 2, 0).contiguous()
+
+        def zero_outside_image(rows):              # the next convolution's zero padding / no gradient out there
+            if top:
+                rows[:D].zero_()
+            if bottom:
+                rows[-D:].zero_()
+
+        a0 = torch.zeros((hb + 2 * D, W, C1), dtype=torch.float64)
+        a0[D:-D] = x[0, :, r0:r1].permute(1, 2, 0)
+        parallel.halo_exchange(grp, a0, depth=D)                  # v = 2
+        a1 = whole_band_conv(a0, w1)                              # v = 1: the outermost rows are junk
+        zero_outside_image(a1)
+        y = whole_band_conv(a1, w2)                               # v = 0: only the owned rows are right
+        fwd_err = float((y[D:-D] - yr[0, :, r0:r1].permute(1, 2, 0)).abs().max())
+        g1 = torch.full((hb + 2 * D, W, C1), float('nan'), dtype=torch.float64)
+        g1[D:-D] = gout[0, :, r0:r1].permute(1, 2, 0)
+        parallel.halo_exchange(grp, g1, zero_border=True, depth=D)   # u = 2
+        g0 = whole_band_bwd(g1, w2, C2)                           # u = 1
+        zero_outside_image(g0)                                    # (the ReLU mask does this on the product path)
+        gx = whole_band_bwd(g0, w1, C1)                           # u = 0
+        bwd_err = float((gx[D:-D] - gref[0, :, r0:r1].permute(1, 2, 0)).abs().max())
+        out[rank] = (fwd_err, bwd_err)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_two_row_halos_serve_two_convolutions_over_gloo(world):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_halo2_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert sorted(out.keys()) == list(range(world))
+    for rank in range(world):
+        fwd_err, bwd_err = out[rank]
+        assert fwd_err < 1e-10 and bwd_err < 1e-10, (rank, fwd_err, bwd_err)
+
+
+def test_halo_schedule_of_the_vgg19_path():
+    """parallel.halo_schedule: with one halo row every convolution but the first waits for its neighbours (12 forward +
+    13 backward exchanges up to conv5_1); with two rows every second one does (6 + 7), and the steps in between run
+    their tap gradients on the owned rows +- 1."""
+    from artstyletransfer_b200.parallel import PyramidBands, halo_schedule
+    kinds = ['conv', 'conv', 'pool', 'conv', 'conv', 'pool', 'conv', 'conv', 'conv', 'conv', 'pool',
+             'conv', 'conv', 'conv', 'conv', 'pool', 'conv']
+    taps = {0: (0,), 3: (1,), 6: (2,), 11: (3,), 12: ('content',), 16: (4,)}
+    convs = [s for s, k in enumerate(kinds) if k == 'conv']
+    f1, b1 = halo_schedule(kinds, taps, 1)
+    assert f1 == set(convs[1:]) and all(b1[s] == ('exchange', 0) for s in convs) and len(b1) == 13
+    f2, b2 = halo_schedule(kinds, taps, 2)
+    assert f2 == {3, 6, 8, 11, 13, 16}                                          # c2_1 c3_1 c3_3 c4_1 c4_3 c5_1
+    assert sorted(s for s in convs if b2[s][0] == 'exchange') == [1, 4, 7, 9, 12, 14, 16]
+    assert all(b2[s] == ('local', 1) for s in (0, 3, 6, 8, 11, 13))
+    # every step that runs locally in the backward reads a forward band that fed a convolution (its halo row is valid)
+    assert all(kinds[s + 1] == 'conv' for s, (how, _) in b2.items() if how == 'local')
+    # taps deeper than the path: nothing flows above the deepest tap
+    _, b = halo_schedule(kinds, {3: (1,)}, 2)
+    assert sorted(b) == [0, 1, 3] and b[3] == ('exchange', 0) and b[1] == ('exchange', 0) and b[0] == ('local', 1)
+    with pytest.raises(ValueError):
+        halo_schedule(kinds, taps, 3)
+    # the depth a plan can carry: every band must own `depth` rows at stride 16
+    assert PyramidBands([(2048, 3072), (1024, 1536), (512, 768), (256, 384)], 8).halo_depth(2) == 2
+    p = PyramidBands([(128, 64)], 4, uniform=True)
+    assert p.halo_depth(2) == 2 and p.halo_depth(1) == 1
+    p.bounds = [[0, 16, 48, 96, 128]]                  # a hand-made plan with a 16-row band: one row at stride 16
+    assert p.halo_depth(2) == 1
+
+
 @pytest.mark.parametrize('edges', [[0, 16, 24], [0, 8, 8, 24], [0, 0, 10, 24]])
 def test_halo_exchange_with_unequal_and_empty_bands_over_gloo(edges):
     """The level-aware plan (parallel.PyramidBands): bands of different heights, and ranks that own no rows of a
@@ -313,6 +411,15 @@ def test_peer_halo_group_pairs_slots_and_counters(monkeypatch):
     assert len(rows) == 16 and calls == 1
     with pytest.raises(ValueError, match='exceeds the staging slot'):
         rows_of(1, [(torch.zeros(4, 64, 32), 0, 2, 0)], False)
+    # two halo rows per exchange: the two edge rows travel as ONE contiguous piece of twice the bytes
+    wide = torch.zeros(10, 8, 4)                                  # 6 owned rows + 2 halo rows per side
+    launched.clear()
+    parallel.halo_exchange(group(1), [(wide, 0, 2, 0)], zero_border=True, depth=2)
+    up2, dn2 = launched['rows']
+    assert up2['src'] == wide[2].data_ptr() and up2['halo'] == wide[0].data_ptr() and up2['bytes'] == 2 * 8 * 4 * 4
+    assert dn2['src'] == wide[6].data_ptr() and dn2['halo'] == wide[8].data_ptr() and dn2['bytes'] == 2 * 8 * 4 * 4
+    with pytest.raises(ValueError, match='cannot hand 2 rows'):
+        parallel.halo_exchange(group(1), [(torch.zeros(5, 8, 4), 0, 2, 0)], depth=2)
 
 
 @pytest.mark.parametrize('world', [2, 3, 4, 8])
