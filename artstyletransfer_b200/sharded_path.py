@@ -30,6 +30,7 @@ from . import parallel as par
 
 _CL = torch.channels_last
 MULTI_STREAM = os.environ.get('AST_LEVEL_STREAMS', '1') != '0'
+LANE_PRIORITY = int(os.environ.get('AST_LANE_PRIORITY', '0'))
 # '1': the band convolutions run as cuDNN's fused conv + bias + ReLU over the WHOLE padded band with symmetric
 # padding — (h + 2) rows in, (h + 2) rows out; the h owned rows only ever see real rows (their halos), the two outer
 # output rows saw the zero padding, are junk, and are exactly the halo rows of the next layer: the next exchange
@@ -52,7 +53,9 @@ class Lanes:
 
     def __init__(self, device: torch.device, n: int):
         self.device = device
-        self.side = [torch.cuda.Stream(device) for _ in range(max(n - 1, 0))]
+        # AST_LANE_PRIORITY=-1 runs the small levels' lanes at high priority; measured on a B200 it changes nothing
+        # (tests/tools/rank_time_probe.py: 4.05 vs 4.06 ms for the two-band rank), so the default stays 0
+        self.side = [torch.cuda.Stream(device, priority=LANE_PRIORITY) for _ in range(max(n - 1, 0))]
 
     def each(self, indices, fn) -> None:
         """fn(li) for every li in indices; li == indices[0] on the current stream, the rest on side streams."""
