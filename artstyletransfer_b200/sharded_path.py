@@ -1,21 +1,27 @@
 """Row-band sharded levels on the channels-last feature path, with per-layer halo exchange.
 
 A rank owns a band of rows of a level (which rows of which level: parallel.PyramidBands; band edges are multiples of
-16 so the four 2x2 max-pools never straddle ranks; a rank may own nothing of a level) and ONLY computes those:
-before each 3x3 convolution it swaps one activation row with each neighbour (parallel.halo_exchange; rows are
-contiguous in NHWC, so they go over NVLink in place, no packing).  The backward uses the SAME exchange on the
-gradient w.r.t. each convolution's output: with the neighbours' edge gradient rows in the halos, an ordinary
-symmetric-padding backward-data convolution over the padded band yields complete gradients for the owned rows (its
-two halo output rows are incomplete and ignored) — cuDNN's asymmetric-padding backward-data, which the mirrored
-"send halo gradients back" scheme needs, runs 1.5x slower on B200.  The first convolution needs no exchange in the
-forward: every rank holds the whole (3-channel) level image.
+16 so the four 2x2 max-pools never straddle ranks; a rank may own nothing of a level) and ONLY computes those plus
+its halo rows: a 3x3 convolution needs one activation row of each neighbour (parallel.halo_exchange; rows are
+contiguous in NHWC, so they go over NVLink in place, no packing).  A band carries D halo rows per side
+(parallel.halo_schedule): with D = 2 one exchange serves two stacked convolutions — the first one leaves one valid,
+redundantly computed halo row — so only every second convolution waits for the neighbours.  The backward uses the
+SAME exchange on the gradient w.r.t. each convolution's output: with the neighbours' edge gradient rows in the halos,
+an ordinary symmetric-padding backward-data convolution over the padded band yields complete gradients for the owned
+rows (and, with D = 2, for one halo row per side, on which the next step applies its tap gradients and ReLU mask
+itself) — cuDNN's asymmetric-padding backward-data, which the mirrored "send halo gradients back" scheme needs, runs
+1.5x slower on B200.  The first convolution needs no exchange in the forward: every rank holds the whole (3-channel)
+level image.
 
-Activations live in padded bands (row 0 / row h+1 are the halos; at the image border they are zero = the
-convolution's zero padding).  The convolutions run as cuDNN's fused conv + bias + ReLU over the whole padded band
-(FUSED_BAND_CONV): the two outer output rows are junk and are exactly the halo rows the next exchange overwrites.
+Activations live in padded bands (D halo rows above and below the owned rows; at the image border they are zero =
+the convolution's zero padding).  The convolutions run as cuDNN's fused conv + bias + ReLU over the whole padded band
+(FUSED_BAND_CONV): the outermost output row per side saw the band's zero padding instead of a real row and is junk —
+with D = 1 exactly the halo row the next exchange overwrites, with D = 2 the row the second convolution of a pair
+does not need.
 
-Per closure: 12 + 13 grouped send/recv steps for ALL levels of the rank (<= 0.8 MB per row), ONE all-reduce(sum) of
-the packed raw Grams + content SSE of all levels (~2.4 MB per level), then every rank finalises identically.
+Per closure (D = 2): 6 + 7 exchanges for ALL levels of the rank (two rows, <= 1.6 MB per side), per-tap all-reduces
+(sum) of the packed raw Grams + content SSE of all levels overlapped with the layers above the tap, then every rank
+finalises identically.
 """
 from __future__ import annotations
 
@@ -234,7 +240,7 @@ def sharded_backward(state, g_total) -> torch.Tensor:
 class ShardedPyramid:
     """All sharded levels of a job evaluated in LOCK-STEP: the pyramid levels' feature paths do not depend on one
     another, so step s of every level runs before step s+1 of any, and the halo rows of all levels travel in ONE
-    grouped send/recv per step (13 + 13 per closure instead of 13 + 13 per level), the raw Grams of all levels in
+    grouped exchange per step (6 + 7 per closure with two-row halos, not per level), the raw Grams of all levels in
     ONE all-reduce.  A send/recv group costs ~30 us of latency on NVLink whatever it carries (rows are <= 0.8 MB)."""
 
     def __init__(self, levels: List[ShardedPathLevel]):
