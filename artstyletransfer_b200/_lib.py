@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libast_sm100.so')
 
-AST_ABI_VERSION = 8
+AST_ABI_VERSION = 9
 AST_PREC_TF32, AST_PREC_FP32, AST_PREC_BF16 = 0, 1, 2
 AST_LAYOUT_CHW, AST_LAYOUT_HWC = 0, 1
 AST_COORD_TORCH, AST_COORD_CV2 = 0, 1
@@ -84,6 +84,7 @@ SIGNATURES = {
     'ast_unprepare_hwc': (_i, [_p, _i64, _d, _d, _d, _p, _p]),
     'ast_tv_fwd': (_i, [_p, _i, _i, _i, _p, _p, _p, _sz, _p]),
     'ast_tv_bwd': (_i, [_p, _i, _i, _i, _p, _f, _f, _p, _p, _i, _p]),
+    'ast_tv_bwd_rows': (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _i, _p]),
     'ast_level_combine': (_i, [_p, _i, _p, _p, _f, _f, _f, _p, _p]),
     'ast_bicubic_down2x': (_i, [_p, _i, _i, _i, _p, _p]),
     'ast_bicubic_down2x_adj': (_i, [_p, _i, _i, _i, _p, _i, _p]),

@@ -152,17 +152,20 @@ __device__ __forceinline__ float sgn(float v) { return (float)((v > 0.f) - (v < 
 __global__ void __launch_bounds__(kThreads) tv_bwd_kernel(const float* __restrict__ Y, int C, int H, int W,
                                                          const float* __restrict__ sums2, float kx, float ky,
                                                          const float* __restrict__ gscale, float* __restrict__ dY,
-                                                         int accumulate, int vec_ok) {
+                                                         int accumulate, int vec_ok, int r0, int r1) {
+  // rows [r0, r1) of every plane (the whole image: 0, H); neighbours outside the range are still read
   const float gs = gscale ? __ldg(gscale) : 1.f;
   const float cx = kx * sums2[0] * gs, cy = ky * sums2[1] * gs;
-  const int64_t n = (int64_t)C * H * W;
+  const int hb = r1 - r0;
+  const int64_t n = (int64_t)C * hb * W;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   if (vec_ok) {
     // 4 consecutive pixels of a row per thread: 16-byte loads of the row, the row above and the row below
     const int w4 = W >> 2;
-    const int64_t rows = (int64_t)C * H;
-    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-     const int y = (int)(row % H);
+    const int64_t rows = (int64_t)C * hb;
+    for (int64_t rr = blockIdx.x; rr < rows; rr += gridDim.x) {
+     const int y = r0 + (int)(rr % hb);
+     const int64_t row = (rr / hb) * H + y;
 #pragma unroll 2
      for (int xq = threadIdx.x; xq < w4; xq += blockDim.x) {
       const float* p = Y + row * W + (xq << 2);
@@ -195,10 +198,11 @@ __global__ void __launch_bounds__(kThreads) tv_bwd_kernel(const float* __restric
     }
     return;
   }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
-    const int64_t row = i / W;
-    const int x = (int)(i - row * W);
-    const int y = (int)(row % H);
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += nthreads) {
+    const int64_t rr = j / W;
+    const int x = (int)(j - rr * W);
+    const int y = r0 + (int)(rr % hb);
+    const int64_t i = ((rr / hb) * H + y) * W + x;
     const float a = __ldg(Y + i);
     float g = 0.f;
     if (x + 1 < W) g += cx * sgn(a - __ldg(Y + i + 1));
@@ -285,6 +289,20 @@ extern "C" int ast_tv_bwd(const float* Y, int C, int H, int W, const float* sums
   if (blocks > 148 * 16) blocks = 148 * 16;
   const int vec_ok = aligned16(Y) && aligned16(dY) && (W % 4 == 0);
   tv_bwd_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(Y, C, H, W, sums2, kx, ky, gscale, dY, accumulate,
-                                                                    vec_ok);
+                                                                    vec_ok, 0, H);
   return check_launch("ast_tv_bwd");
+}
+
+extern "C" int ast_tv_bwd_rows(const float* Y, int C, int H, int W, int r0, int r1, const float* sums2, float kx,
+                               float ky, const float* gscale, float* dY, int accumulate, void* stream) {
+  AST_REQUIRE(Y && sums2 && dY, AST_ERR_INVALID, "ast_tv_bwd_rows: null pointer");
+  AST_REQUIRE(C > 0 && H > 0 && W > 0, AST_ERR_INVALID, "ast_tv_bwd_rows: bad shape %dx%dx%d", C, H, W);
+  AST_REQUIRE(0 <= r0 && r0 < r1 && r1 <= H, AST_ERR_INVALID, "ast_tv_bwd_rows: rows [%d, %d) of %d", r0, r1, H);
+  const int64_t n = (int64_t)C * (r1 - r0) * W;
+  int64_t blocks = (n + (int64_t)kThreads * 4 - 1) / ((int64_t)kThreads * 4);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const int vec_ok = aligned16(Y) && aligned16(dY) && (W % 4 == 0);
+  tv_bwd_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(Y, C, H, W, sums2, kx, ky, gscale, dY, accumulate,
+                                                                    vec_ok, r0, r1);
+  return check_launch("ast_tv_bwd_rows");
 }

@@ -68,7 +68,7 @@ STATS = KernelStats()
 
 # kernels launched per C-ABI entry point
 _KERNELS_PER_CALL = {'ast_gram_mse_fwd': 2, 'ast_gram_mse_fwd_nhwc': 2, 'ast_gram_bwd_nhwc': 1, 'ast_gram_bwd_nhwc_bf16': 1, 'ast_gram_finalize': 1, 'ast_gram_finalize_batch': 1, 'ast_gram_bwd': 1, 'ast_mse_fwd': 1, 'ast_mse_bwd': 1,
-                     'ast_tv_fwd': 1, 'ast_tv_bwd': 1, 'ast_level_combine': 1, 'ast_bicubic_down2x': 1, 'ast_bicubic_down2x_tv': 1,
+                     'ast_tv_fwd': 1, 'ast_tv_bwd': 1, 'ast_tv_bwd_rows': 1, 'ast_level_combine': 1, 'ast_bicubic_down2x': 1, 'ast_bicubic_down2x_tv': 1,
                      'ast_bicubic_down2x_adj': 1, 'ast_bicubic_resize': 1, 'ast_bicubic_resize_adj': 1,
                      'ast_noise_init': 1, 'ast_bias_relu_nhwc': 1, 'ast_relu_bwd': 1, 'ast_maxpool2x2_nhwc': 1,
                      'ast_maxpool2x2_bwd_nhwc': 1, 'ast_chw_to_hwc': 1, 'ast_hwc_to_chw': 1, 'ast_unprepare_hwc': 1, 'ast_halo_exchange': 1, 'ast_band_announce': 1, 'ast_band_gather': 1}
@@ -436,11 +436,18 @@ def tv_fwd(y, sums2, tv, ws):
             tv.data_ptr() if tv is not None else None, ws.ptr, ws.nbytes)
 
 
-def tv_bwd(y, sums2, weight, gscale, dy, accumulate):
+def tv_bwd(y, sums2, weight, gscale, dy, accumulate, rows=None):
+    """rows = (r0, r1): only those rows of every plane (ast_tv_bwd_rows); the scale is the whole image's."""
     dev = y.device
     h, w = y.shape[-2], y.shape[-1]
     c = y.numel() // (h * w)
     nx, ny = float(c) * h * (w - 1), float(c) * (h - 1) * w
+    if rows is not None:
+        r0, r1 = int(rows[0]), int(rows[1])
+        _launch(dev, ('tv_bwd_rows', c * (r1 - r0) * w), 'ast_tv_bwd_rows', y.data_ptr(), c, h, w, r0, r1, sums2.data_ptr(),
+                2.0 * weight / (nx * nx), 2.0 * weight / (ny * ny), gscale.data_ptr() if gscale is not None else None,
+                dy.data_ptr(), int(accumulate))
+        return
     _launch(dev, ('tv_bwd', y.numel()), 'ast_tv_bwd', y.data_ptr(), c, h, w, sums2.data_ptr(), 2.0 * weight / (nx * nx),
             2.0 * weight / (ny * ny), gscale.data_ptr() if gscale is not None else None, dy.data_ptr(),
             int(accumulate))

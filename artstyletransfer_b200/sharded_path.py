@@ -535,8 +535,8 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL, gather=None) -> Lis
     d_imgs = []
     for li, (sh, _, _, im, sums2) in enumerate(state):
         if gather is not None:
-            # peer-memory gather: this rank's rows go straight into the symmetric gradient buffer; everybody's rows
-            # arrive there with gather.gather(), the (replicated) TV gradient is added afterwards on every rank
+            # peer-memory gather: this rank's rows go straight into the symmetric gradient buffer, the TV gradient of
+            # those rows is added in place, and everybody's rows arrive there with gather.gather()
             d = gather.views[li]
         elif grp.rank == 0:                     # TV is replicated: count its gradient once
             d = torch.empty_like(im)
@@ -586,6 +586,9 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL, gather=None) -> Lis
                     c0 = gxp.shape[1]
                     ops.hwc_to_chw(gxp, d_imgs[li], c0, sh.hb * sh.W, gather is None, plane=sh.H * sh.W,
                                    x_off=D * sh.W * c0, y_off=sh.r0 * sh.W)
+                    if gather is not None:      # the TV gradient of MY rows travels with them (the image is replicated)
+                        _, _, _, im, sums2 = state[li]
+                        ops.tv_bwd(im, sums2, sh.weights[2], gsc, d_imgs[li], True, rows=(sh.r0, sh.r1))
                     gps[li] = None
 
             lanes.each(live, dgrad)
@@ -605,7 +608,5 @@ def pyramid_backward(state, g_total, lanes: Lanes = _SERIAL, gather=None) -> Lis
             lanes.each(live, pool)
     if gather is not None:
         with ops.timed(dev, ('gather_image_grad', len(d_imgs))):
-            gather.gather()                     # every rank's rows of every level, in place
-        for (sh, _, _, im, sums2), d in zip(state, d_imgs):
-            ops.tv_bwd(im, sums2, sh.weights[2], gsc, d, True)
+            gather.gather()                     # every rank's rows of every level (TV gradient included), in place
     return d_imgs

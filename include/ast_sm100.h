@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 8
+#define AST_ABI_VERSION 9
 
 #define AST_OK               0
 #define AST_ERR_INVALID     -1   /* bad argument (null pointer, non-positive size, misalignment) */
@@ -231,6 +231,11 @@ int ast_tv_fwd(const float* Y, int C, int H, int W, float* sums2, float* tv, voi
                size_t ws_bytes, void* stream);
 int ast_tv_bwd(const float* Y, int C, int H, int W, const float* sums2, float kx, float ky,
                const float* gscale, float* dY, int accumulate, void* stream);
+/* The same for rows [r0, r1) of every plane only (Y and dY are still the whole (C, H, W) tensors; the rows above r0
+ * and below r1 - 1 are read as neighbours): a rank of a row-band sharded job adds the TV gradient of the rows it owns
+ * before the image-gradient gather instead of every rank adding all of it afterwards. */
+int ast_tv_bwd_rows(const float* Y, int C, int H, int W, int r0, int r1, const float* sums2, float kx,
+                    float ky, const float* gscale, float* dY, int accumulate, void* stream);
 
 /* ---- Level loss assembly (neural_style_transfer.py:100-110) ---------------------------------
  *   out4 = { total, content, style, tv } with style = mean(style_mse[0..n_style)) and

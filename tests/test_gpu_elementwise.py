@@ -57,6 +57,32 @@ def test_total_variation_fwd_bwd(shape):
     assert rel(yd.grad.cpu().numpy(), 3.0 * ref_grad) < 1e-6
 
 
+@pytest.mark.parametrize('shape,rows', [((3, 64, 48), (16, 48)), ((3, 64, 48), (0, 64)), ((3, 33, 7), (1, 2)),
+                                        ((3, 33, 7), (30, 33)), ((1, 8, 12), (0, 3))])
+def test_tv_bwd_rows_is_the_full_gradient_on_those_rows(shape, rows):
+    """ast_tv_bwd_rows (a sharded rank adds the TV gradient of ITS rows before the gather): bit-identical to the rows
+    of ast_tv_bwd's result, every other row untouched; vectorised (W % 4 == 0) and scalar paths, accumulate or not."""
+    from artstyletransfer_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    y = torch.randn((1, *shape), generator=g).to(dev())
+    sums2 = torch.empty(2, device=dev())
+    tv = torch.empty(1, device=dev())
+    ops.tv_fwd(y, sums2, tv, ops.reduce_workspace(dev()))
+    gs = torch.tensor([0.7], device=dev())
+    full = torch.empty_like(y)
+    ops.tv_bwd(y, sums2, 100.0, gs, full, False)
+    r0, r1 = rows
+    for accumulate in (False, True):
+        base = torch.randn(y.shape, generator=g).to(dev())
+        out = base.clone()
+        ops.tv_bwd(y, sums2, 100.0, gs, out, accumulate, rows=rows)
+        want = base.clone()
+        want[:, :, r0:r1] = (base[:, :, r0:r1] + full[:, :, r0:r1]) if accumulate else full[:, :, r0:r1]
+        assert torch.equal(out, want)
+    with pytest.raises(Exception, match='rows'):
+        ops.tv_bwd(y, sums2, 1.0, None, full, False, rows=(r1, r1))
+
+
 def test_total_variation_golden(golden):
     from artstyletransfer_b200 import math_utils
     gd = golden('small_ops.npz')
