@@ -68,6 +68,7 @@ ASYNC_YIELD = os.environ.get('AST_ASYNC_YIELD', '1') != '0'
 # Row-band sharding: every rank runs the same loop and holds the same image; only rank 0 copies it to the host
 # (the other ranks yield None for the image) unless this is set.
 YIELD_ON_ALL_RANKS = os.environ.get('AST_YIELD_ALL_RANKS', '0') == '1'
+YIELD_PREWARM = int(os.environ.get('AST_YIELD_PREWARM', '6'))     # page-locked blocks cached at job start (_ImageYielder)
 
 # The reference runs up to simultaneous_tasks_count = 2 jobs in one process (config.py:1, task_executor.py:9): their
 # closures come from different executor threads, all on the device's default (legacy) stream.  While one job captures
@@ -446,6 +447,12 @@ class _ImageYielder:
             with _GPU_SETUP_LOCK:
                 self.stage = [torch.empty(self.shape, dtype=torch.float32, device=dev) for _ in range(2)]
                 self.side = torch.cuda.Stream(dev)
+                # Every yield hands out a FRESH page-locked block (the consumer may keep the array).  Torch's host
+                # allocator caches freed blocks, but page-locking a new 75 MB block costs tens of milliseconds — ten
+                # 8-GPU steps.  Fill the cache now with as many blocks as are ever alive at once (consumer's current
+                # and previous image, the look-ahead copy in flight, blocks whose copy event is still pending).
+                warm = [torch.empty(self.shape, dtype=torch.float32, pin_memory=True) for _ in range(YIELD_PREWARM)]
+                del warm
             self.drained = [None, None]      # event: the copy that last read stage[i] has finished
 
     def begin(self):

@@ -215,6 +215,17 @@ def kernel_work(key):
     return 0.0, 0.0
 
 
+def _gap_summary(times, warmup):
+    """Wall-clock gaps between consecutive yields of the timed region: median, max and where the max was."""
+    gaps = [1e3 * (b - a) for a, b in zip(times[warmup - 1:-1], times[warmup:])]
+    if not gaps:
+        return None
+    srt = sorted(gaps)
+    worst = max(range(len(gaps)), key=gaps.__getitem__)
+    return {'median': round(srt[len(srt) // 2], 3), 'max': round(gaps[worst], 3), 'max_at_timed_step': worst + 1,
+            'over_3x_median': sum(1 for g in gaps if g > 3 * srt[len(srt) // 2])}
+
+
 def ncu_traffic(kernel: str):
     """DRAM bytes (read + write) of one launch of `kernel` from the committed `ncu --set full` capture of
     tests/tools/ncu_target.py (profiles/r01_ncu_traffic.json; same shapes as the L=3 top level at N=1), or None."""
@@ -442,6 +453,15 @@ def run_ours(args):
         torch.cuda.empty_cache()
 
         first_yield_s = [None]
+        yield_times = []
+        host_allocs = [None, None]        # page-locked allocations (cudaHostAlloc) at the start / end of the timed region
+
+        def _host_allocs():
+            try:
+                st = torch.cuda.host_memory_stats()
+                return int(st.get('num_host_alloc', st.get('host_alloc_count', -1)))
+            except Exception:
+                return -1
 
         async def drive():
             drv = nst.NeuralStyleTransfer(dev, 'vgg19', style_levels, args.optimizer)
@@ -452,13 +472,19 @@ def run_ours(args):
             async for img, step in drv.process(content_levels, init, 10.0, iters, *WEIGHTS, name):
                 n += 1
                 last = (img, step)
+                yield_times.append(time.perf_counter())
                 if n == 1:
                     first_yield_s[0] = time.perf_counter() - t_call
                 if n == args.warmup:
                     barrier()
+                    host_allocs[0] = _host_allocs()
                     t_start = (time.perf_counter(), step)
+            # the clock stops at the LAST YIELD: what follows is the generator's tear-down (CUDA graph, NCCL-capturing
+            # buffers, executor), a once-per-job cost of 0.05-1 s that is not part of a step
+            t_end = yield_times[-1]
             barrier()
-            return t_start, time.perf_counter(), last
+            host_allocs[1] = _host_allocs()
+            return t_start, t_end, last
 
         (t0, step0), t1, (img, step1) = asyncio.run(drive())
         phase('end-to-end pass through process() done')
@@ -470,11 +496,14 @@ def run_ours(args):
         if rank == 0:
             assert img.shape == (H, W, 3) and img.dtype == np.float32
         e2e = {'value': (step1 - step0) / wall, 'unit': UNIT, 'h2d_bytes_per_step': 0,
-               'd2h_bytes_per_step': int(H * W * 3 * 4), 'timed': 'wall clock around K optimizer steps of '
-               'NeuralStyleTransfer.process() incl. the per-step image yield (device->host into page-locked memory, '
+               'd2h_bytes_per_step': int(H * W * 3 * 4), 'timed': 'wall clock from yield W to yield W+K of '
+               'NeuralStyleTransfer.process(), max over ranks, incl. the per-step image yield (device->host into page-locked memory, '
                'overlapped with the next step; rank 0 copies under sharding); job inputs uploaded once at setup',
                'setup_h2d_bytes': int(sum(a.nbytes for a in content_levels + style_levels) + init.nbytes),
-               'setup_plus_first_step_s': round(first_yield_s[0], 3) if first_yield_s[0] else None}
+               'setup_plus_first_step_s': round(first_yield_s[0], 3) if first_yield_s[0] else None,
+               'yield_gaps_ms': _gap_summary(yield_times, args.warmup),
+               'page_locked_allocs_in_timed_region': (host_allocs[1] - host_allocs[0]
+                                                      if None not in host_allocs and min(host_allocs) >= 0 else None)}
 
     if world > 1:
         # CUDA graphs hold captured NCCL kernels: release them before the communicator goes away
