@@ -17,6 +17,7 @@ from __future__ import annotations
 import asyncio
 import concurrent.futures
 import os
+import time
 import threading
 import traceback
 
@@ -68,7 +69,8 @@ ASYNC_YIELD = os.environ.get('AST_ASYNC_YIELD', '1') != '0'
 # Row-band sharding: every rank runs the same loop and holds the same image; only rank 0 copies it to the host
 # (the other ranks yield None for the image) unless this is set.
 YIELD_ON_ALL_RANKS = os.environ.get('AST_YIELD_ALL_RANKS', '0') == '1'
-YIELD_PREWARM = int(os.environ.get('AST_YIELD_PREWARM', '6'))     # page-locked blocks cached at job start (_ImageYielder)
+YIELD_TRACE = [] if os.environ.get('AST_YIELD_TRACE', '0') == '1' else None   # (what, step, host ms) per step, for bench.py
+YIELD_PREWARM = int(os.environ.get('AST_YIELD_PREWARM', '4'))     # page-locked blocks cached at job start (_ImageYielder)
 
 # The reference runs up to simultaneous_tasks_count = 2 jobs in one process (config.py:1, task_executor.py:9): their
 # closures come from different executor threads, all on the device's default (legacy) stream.  While one job captures
@@ -406,8 +408,18 @@ class NeuralStyleTransfer:
             """Executor thread: one optimizer step, then the snapshot of its image — enqueued back to back under the
             GPU lock, so the next step (this job's or another job's) cannot slip in between."""
             with _GPU_SETUP_LOCK:
+                t_step = time.perf_counter()
+                had_graph = job._graph is not None
                 job.optimizer_step()
-                return yielder.begin(), job.step
+                if job._graph is not None and not had_graph:
+                    yielder.prewarm()        # the capture emptied torch's page-locked cache
+                t_snap = time.perf_counter()
+                ticket = yielder.begin()
+                if YIELD_TRACE is not None:
+                    now = time.perf_counter()
+                    YIELD_TRACE.append(('optimizer_step_host', job.step, 1e3 * (t_snap - t_step)))
+                    YIELD_TRACE.append(('snapshot_host', job.step, 1e3 * (now - t_snap)))
+                return ticket, job.step
 
         pending = loop.run_in_executor(worker, step_and_snapshot) if job.step < iters_num else None
         try:
@@ -447,13 +459,22 @@ class _ImageYielder:
             with _GPU_SETUP_LOCK:
                 self.stage = [torch.empty(self.shape, dtype=torch.float32, device=dev) for _ in range(2)]
                 self.side = torch.cuda.Stream(dev)
-                # Every yield hands out a FRESH page-locked block (the consumer may keep the array).  Torch's host
-                # allocator caches freed blocks, but page-locking a new 75 MB block costs tens of milliseconds — ten
-                # 8-GPU steps.  Fill the cache now with as many blocks as are ever alive at once (consumer's current
-                # and previous image, the look-ahead copy in flight, blocks whose copy event is still pending).
-                warm = [torch.empty(self.shape, dtype=torch.float32, pin_memory=True) for _ in range(YIELD_PREWARM)]
-                del warm
             self.drained = [None, None]      # event: the copy that last read stage[i] has finished
+            self.prewarm(min(YIELD_PREWARM, 3))
+
+    def prewarm(self, n: int = None):
+        """Every yield hands out a FRESH page-locked block (the consumer may keep the array).  Torch's host allocator
+        caches freed blocks, but page-locking a new 75 MB block costs ~50 ms (measured on the B200 boxes) — ten 8-GPU
+        steps.  Fill the cache with as many blocks as are ever alive at once (the consumer's current and previous
+        image, the look-ahead copy in flight, blocks whose copy event is still pending).  Called at job start, and
+        AGAIN right after the closure's CUDA graph has been captured: torch.cuda.graph() empties the page-locked cache
+        (torch._C._host_emptyCache) on entry, which used to put three fresh allocations into the steps after it."""
+        if not self.active:
+            return
+        with _GPU_SETUP_LOCK:
+            warm = [torch.empty(self.shape, dtype=torch.float32, pin_memory=True)
+                    for _ in range(YIELD_PREWARM if n is None else n)]
+            del warm
 
     def begin(self):
         if not self.active:
@@ -471,8 +492,11 @@ class _ImageYielder:
             self.stage[i].copy_(((self.img.detach() + mean) / 255).permute([0, 2, 3, 1]).squeeze(0))
         ready = torch.cuda.Event()
         ready.record(main)
+        t_alloc = time.perf_counter()
         with _GPU_SETUP_LOCK:                # a pinned block may be a fresh cudaHostAlloc: not during a capture
             host = torch.empty(self.shape, dtype=torch.float32, pin_memory=True)
+        if YIELD_TRACE is not None:
+            YIELD_TRACE.append(('page_locked_block', self.n, 1e3 * (time.perf_counter() - t_alloc)))
         self.side.wait_event(ready)
         with torch.cuda.stream(self.side):
             host.copy_(self.stage[i], non_blocking=True)

@@ -463,6 +463,18 @@ def run_ours(args):
             except Exception:
                 return -1
 
+        import gc
+        gc_log, gc_t0 = [], [0.0]       # (generation, pause ms, wall time) of every collection during the pass
+
+        def gc_cb(phase, info):
+            if phase == 'start':
+                gc_t0[0] = time.perf_counter()
+            else:
+                now = time.perf_counter()
+                gc_log.append((info.get('generation'), 1e3 * (now - gc_t0[0]), now))
+
+        gc.callbacks.append(gc_cb)
+
         async def drive():
             drv = nst.NeuralStyleTransfer(dev, 'vgg19', style_levels, args.optimizer)
             n, t_start, last = 0, None, None
@@ -487,6 +499,8 @@ def run_ours(args):
             return t_start, t_end, last
 
         (t0, step0), t1, (img, step1) = asyncio.run(drive())
+        gc.callbacks.remove(gc_cb)
+        gc_timed = [(g, round(ms, 2)) for g, ms, t in gc_log if t0 <= t <= t1 and ms >= 1.0]
         phase('end-to-end pass through process() done')
         wall = t1 - t0
         if world > 1:
@@ -502,6 +516,9 @@ def run_ours(args):
                'setup_h2d_bytes': int(sum(a.nbytes for a in content_levels + style_levels) + init.nbytes),
                'setup_plus_first_step_s': round(first_yield_s[0], 3) if first_yield_s[0] else None,
                'yield_gaps_ms': _gap_summary(yield_times, args.warmup),
+               'python_gc_pauses_over_1ms_in_timed_region': gc_timed,
+               'host_trace_over_5ms': ([(w, st, round(ms, 2)) for w, st, ms in nst.YIELD_TRACE if ms > 5.0]
+                                       if nst.YIELD_TRACE is not None else None),
                'page_locked_allocs_in_timed_region': (host_allocs[1] - host_allocs[0]
                                                       if None not in host_allocs and min(host_allocs) >= 0 else None)}
 
