@@ -5,15 +5,17 @@ an identical optimizer.  The default scheme (sharded_path.ShardedPathLevel on th
 
   * PyramidBands deals the rows of the WHOLE pyramid out to the ranks (a rank owns a band of one or two levels; at 8
     ranks the 2048x3072 level sits on six of them and the three lower levels on the other two);
-  * a rank computes exactly its rows and exchanges ONE halo row with each neighbour before every 3x3 convolution
-    (and the mirrored gradient rows in the backward) — no redundant convolution work;
+  * a rank computes its rows plus two halo rows per side and exchanges those with each neighbour before every
+    SECOND 3x3 convolution (halo_schedule; the mirrored gradient rows in the backward): 13 neighbour synchronisations
+    per closure; the rows travel through NVLink peer memory (PeerHaloGroup) or a grouped NCCL send/recv;
   * the RAW partial Grams F_r F_r^T of the bands (the Gram's K dimension is the spatial index, so the full Gram is
-    the plain sum over ranks) and the partial content SSE of all levels join ONE all-reduce(sum) of the packed buffer
-    [G1 | G2 | G3 | G4 | G5 | content_sse] per level (~2.4 MB each); every rank finalises identically: 1/(C*HW),
-    minus target, MSE, weighted total; the backward dF_r = s (G - A) F_r is rank-local;
-  * the image gradients of all ranks are all-reduced once per closure so the replicated optimizers stay
-    bit-identical.  Total variation is evaluated on the whole (small) level image by every rank; only rank 0
-    contributes its gradient.
+    the plain sum over ranks) and the partial content SSE of all levels are all-reduced (sum) tap by tap under the
+    convolutions above the tap; every rank finalises identically: 1/(C*HW), minus target, MSE, weighted total; the
+    backward dF_r = s (G - A) F_r is rank-local;
+  * the rows of the image-gradient pyramid owned by different ranks are disjoint: they are gathered through peer
+    memory (PeerGradGather; an all-reduce over NCCL without it) so the replicated optimizers stay bit-identical.
+    The total variation VALUE is evaluated on the whole level image by every rank; its gradient is added by the
+    owner of each row before the gather (by rank 0 on the all-reduce path).
 
 The older scheme (ShardedLevel below: torch modules + autograd around the NCHW kernels, used for fp32 precision)
 cuts every level into `world` equal bands, pads each with an 80-row halo (>= the 78-row receptive-field radius of

@@ -443,6 +443,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = closures / (ms * 1e-3)
+    loss_closures = job.step                        # warm-up + timed + per-kernel pass (+ 3 with --profile)
     loss_now = float(job.closure().item())          # collective under sharding: every rank evaluates
     mem_gb = torch.cuda.max_memory_allocated(dev) / 1e9
 
@@ -580,7 +581,7 @@ def run_ours(args):
         'other_bracketed_ms_per_step': other,
         'per_rank_busy_ms_eager_pass': per_rank_busy,
         'setup_kernels': kernel_table(setup_kernels, pk)[:8],
-        'init_image_s': round(init_s, 4), 'loss_after': loss_now, 'parity': parity,
+        'init_image_s': round(init_s, 4), 'loss_after': loss_now, 'loss_after_closures': loss_closures, 'parity': parity,
         # `value` counts reference iterations (closures: what iters_num counts); LBFGS takes two per optimizer.step
         'closures_per_s': round(value, 4),
         'optimizer_steps_per_s': round(value / (2 if args.optimizer == 'lbfgs' else 1), 4),
