@@ -270,6 +270,62 @@ def test_halo_schedule_of_the_vgg19_path():
     assert p.halo_depth(2) == 1
 
 
+def test_halo_schedule_keeps_every_read_row_valid_for_any_network():
+    """Property test of parallel.halo_schedule on random conv / pool sequences with random taps: replay the validity
+    bookkeeping the docstring describes and check that (forward) no convolution ever reads an invalid halo row into an
+    owned row, (backward) every step that runs without an exchange finds both the gradient band and the forward band
+    valid on the rows it touches, and that depth 2 never exchanges more often than depth 1."""
+    from hypothesis import given, settings, strategies as st
+    from artstyletransfer_b200.parallel import halo_schedule
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.sampled_from(['conv', 'conv', 'conv', 'pool']), min_size=1, max_size=24), st.data())
+    def check(kinds, data):
+        kinds = ['conv'] + kinds                                   # the path starts with a convolution of the image
+        taps = set(data.draw(st.lists(st.integers(0, len(kinds) - 1), min_size=1, max_size=6)))
+        taps = {s for s in taps if kinds[s] == 'conv'} or {0}       # taps are ReLU outputs
+        counts = {}
+        for depth in (1, 2):
+            fwd, bwd = halo_schedule(kinds, {s: (0,) for s in taps}, depth)
+            # forward replay: valid[s] = valid halo rows of step s's OUTPUT band when the backward reads it
+            v, valid = depth, {}
+            for s, kind in enumerate(kinds):
+                if kind == 'conv':
+                    if s in fwd:
+                        assert s > 0 and v < 1
+                        valid[s - 1] = depth                        # the exchange overwrote the input band's halos
+                        v = depth
+                    assert v >= 1, (kinds, s)                       # the owned rows' neighbours are real rows
+                    v -= 1
+                else:
+                    assert s not in fwd
+                    v = 0
+                valid[s] = v
+            # backward replay
+            u, flowing, deepest = 0, False, max(taps)
+            for s in range(len(kinds) - 1, -1, -1):
+                if s > deepest:
+                    assert s not in bwd
+                    continue
+                if kinds[s] == 'conv':
+                    how, ext = bwd[s]
+                    if how == 'exchange':
+                        assert ext == 0 and u < 1
+                        u = depth
+                    else:
+                        assert 1 <= ext <= u and valid[s] >= ext, (kinds, taps, s)   # gradient AND activation rows exist
+                        assert s < deepest                          # the first tap gradient has no halo to extend into
+                    u -= 1
+                else:
+                    assert s not in bwd
+                    u = 0
+            assert set(bwd) == {s for s in range(deepest + 1) if kinds[s] == 'conv'}
+            counts[depth] = (len(fwd), sum(1 for h, _ in bwd.values() if h == 'exchange'))
+        assert counts[2][0] <= counts[1][0] and counts[2][1] <= counts[1][1]
+
+    check()
+
+
 @pytest.mark.parametrize('edges', [[0, 16, 24], [0, 8, 8, 24], [0, 0, 10, 24]])
 def test_halo_exchange_with_unequal_and_empty_bands_over_gloo(edges):
     """The level-aware plan (parallel.PyramidBands): bands of different heights, and ranks that own no rows of a
