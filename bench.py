@@ -329,6 +329,12 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     from artstyletransfer_b200 import _lib, neural_style_transfer as nst, ops, parallel
     assert _lib.load().ast_device_check() == 0, _lib.last_error()
+    if args.warmup < 3:
+        # the contract asks for W >= 3; with fewer the closure's CUDA-graph capture (closure GRAPH_WARMUP + 1 = 3: a
+        # once-per-job 0.3 s) would land inside the timed region.  The line reports the warm-up that was run.
+        if rank == 0:
+            print(f'[bench] --warmup {args.warmup} raised to 3 (graph capture happens in closure 3)', file=sys.stderr)
+        args.warmup = 3
     if args.precision:
         nst.PRECISION = args.precision
     from artstyletransfer_b200 import feature_path
