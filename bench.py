@@ -179,7 +179,7 @@ def kernel_work(key):
         return (16.0 if (len(key) > 2 and key[2]) else 12.0) * key[1], 0.0   # X, T (, dX) read; dX written
     if k == 'tv_fwd':
         return 4.0 * key[1], 0.0
-    if k == 'tv_bwd':
+    if k in ('tv_bwd', 'tv_bwd_rows'):     # (name, elements touched): the rows variant counts its own rows only
         return 8.0 * key[1], 0.0
     if k in ('down2x', 'down2x_adj'):
         _, c, h, w = key

@@ -40,4 +40,14 @@ def test_kernel_work_accounting():
     assert bench.kernel_work(('noise_init', 2048, 3072))[0] == 24.0 * 2048 * 3072
     assert bench.kernel_work(('unprepare', 2048 * 3072))[0] == 24.0 * 2048 * 3072
     assert bench.kernel_work(('allreduce_packed_grams', 10)) == (0.0, 0.0)
+    assert bench.kernel_work(('tv_bwd_rows', 3 * 352 * 3072)) == bench.kernel_work(('tv_bwd', 3 * 352 * 3072))
+    assert bench.kernel_work(('tv_bwd_rows', 12))[0] > 0
     assert bench.pixel_ratio(4, 2) == 17.0
+
+
+def test_yield_gap_summary():
+    """e2e diagnostics: gaps between consecutive yields of the timed region (the first `warmup` yields are skipped)."""
+    times = [0.0, 1.0, 2.0, 2.010, 2.020, 2.080, 2.090]              # warm-up 3: timed gaps 10, 10, 60, 10 ms
+    g = bench._gap_summary(times, 3)
+    assert g == {'median': 10.0, 'max': 60.0, 'max_at_timed_step': 3, 'over_3x_median': 1}
+    assert bench._gap_summary([0.0, 1.0], 3) is None
