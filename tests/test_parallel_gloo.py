@@ -240,6 +240,132 @@ def test_two_row_halos_serve_two_convolutions_over_gloo(world):
         assert fwd_err < 1e-10 and bwd_err < 1e-10, (rank, fwd_err, bwd_err)
 
 
+def _band_schedule_worker(rank, world, port, out, depth):
+    """The whole band scheme of sharded_path.pyramid_forward / pyramid_backward restated with torch CPU ops in
+    float64 and run between gloo processes: conv+bias+ReLU over the whole padded band, border zeroing, max-pool of the
+    owned rows, taps, and the backward with tap gradients and ReLU masks on the owned rows +- ext, all driven by
+    parallel.halo_schedule.  Compared with autograd on the whole image."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import torch.nn.functional as F
+        from artstyletransfer_b200 import parallel
+        torch.set_num_threads(2)
+        parallel.init_sharding()
+        grp = parallel._GROUP
+        D = depth
+        H, W = 16 * world, 10
+        kinds = ['conv', 'conv', 'pool', 'conv', 'conv']
+        chans = [3, 4, 5, 5, 6, 4]                       # channels of the input and of every step's output
+        taps = {0: 0.7, 3: -1.3, 4: 0.9}                   # step -> weight of the tap loss 0.5 * w * sum(a_c * y^2)
+        gen = torch.Generator().manual_seed(5)
+        rnd = lambda *shape: torch.randn(shape, generator=gen, dtype=torch.float64)
+        img = rnd(1, chans[0], H, W)
+        ws = {s: (rnd(chans[s + 1], chans[s], 3, 3) * 0.4, rnd(chans[s + 1]) * 0.5 + 0.3)
+              for s, k in enumerate(kinds) if k == 'conv'}
+        a = {s: rnd(chans[s + 1]).abs() + 0.1 for s in taps}
+
+        # ---- reference: the whole image through autograd ------------------------------------------------------
+        xr = img.clone().requires_grad_(True)
+        y, loss_ref = xr, 0.0
+        for s, k in enumerate(kinds):
+            y = F.relu(F.conv2d(y, *ws[s], padding=1)) if k == 'conv' else F.max_pool2d(y, 2)
+            if s in taps:
+                loss_ref = loss_ref + 0.5 * taps[s] * (a[s][None, :, None, None] * y * y).sum()
+        (gref,) = torch.autograd.grad(loss_ref, xr)
+
+        # ---- sharded ------------------------------------------------------------------------------------------
+        fwd_x, bwd_plan = parallel.halo_schedule(kinds, taps, D)
+        top, bottom = rank == 0, rank == world - 1
+        hb = H // world
+        r0 = rank * hb
+        nchw = lambda rows: rows.permute(2, 0, 1)[None]     # (h, W, C) band rows <-> (1, C, h, W)
+        rows_of = lambda t: t[0].permute(1, 2, 0).contiguous()
+
+        def interior(rows, ext=0):
+            return rows[D - ext:rows.shape[0] - D + ext]
+
+        x = torch.zeros((hb + 2 * D, W, chans[0]), dtype=torch.float64)
+        lo, hi = max(r0 - D, 0), min(r0 + hb + D, H)
+        x[lo - (r0 - D):lo - (r0 - D) + hi - lo] = rows_of(img[:, :, lo:hi])
+        bufs, loss_part, n_fwd = [], torch.zeros(1, dtype=torch.float64), 0
+        for s, k in enumerate(kinds):
+            if s in fwd_x:
+                parallel.halo_exchange(grp, x, depth=D)
+                n_fwd += 1
+            if k == 'conv':
+                yb = rows_of(F.relu(F.conv2d(nchw(x), *ws[s], padding=1)))       # the whole padded band
+                if s + 1 < len(kinds) and kinds[s + 1] == 'conv':               # border halos = the next zero padding
+                    if top:
+                        yb[:D] = 0
+                    if bottom:
+                        yb[-D:] = 0
+            else:
+                h2 = (x.shape[0] - 2 * D) // 2
+                yb = torch.full((h2 + 2 * D, W // 2, x.shape[2]), 1e6, dtype=torch.float64)   # halos: junk until exchanged
+                if top:
+                    yb[:D] = 0
+                if bottom:
+                    yb[-D:] = 0
+                yb[D:-D] = rows_of(F.max_pool2d(nchw(interior(x)), 2))
+            if s in taps:
+                yi = interior(yb)
+                loss_part += 0.5 * taps[s] * (a[s] * yi * yi).sum()
+            bufs.append(yb)
+            x = yb
+        dist.all_reduce(loss_part)
+        # backward
+        g, n_bwd, xin = None, 0, None
+        inputs = [None] + bufs[:-1]
+        for s in range(len(kinds) - 1, -1, -1):
+            if s > max(taps):
+                continue
+            yb = bufs[s]
+            if kinds[s] == 'conv':
+                how, ext = bwd_plan[s]
+                if s in taps:
+                    if g is None:
+                        g = torch.full(yb.shape, 1e6, dtype=torch.float64)        # recycled buffer: halos are junk
+                        interior(g)[:] = 0
+                    interior(g, ext)[:] += taps[s] * a[s] * interior(yb, ext)
+                interior(g, ext)[:] *= (interior(yb, ext) > 0)                    # ReLU backward, also on the ext rows
+                if how == 'exchange':
+                    parallel.halo_exchange(grp, g, zero_border=True, depth=D)
+                    n_bwd += 1
+                x_shape = (1, chans[s], yb.shape[0], yb.shape[1])
+                g = rows_of(torch.nn.grad.conv2d_input(x_shape, ws[s][0], nchw(g).contiguous(), padding=1))
+            else:
+                xb = inputs[s]
+                if s in taps:
+                    raise AssertionError('taps are ReLU outputs')
+                xi = nchw(interior(xb)).clone().requires_grad_(True)
+                (gi,) = torch.autograd.grad(F.max_pool2d(xi, 2), xi, nchw(interior(g)).contiguous())
+                g = torch.full(xb.shape, 1e6, dtype=torch.float64)
+                interior(g)[:] = rows_of(gi)
+        mine = nchw(interior(g))
+        want = gref[:, :, r0:r0 + hb]
+        loss_ref = float(loss_ref.detach())
+        out[rank] = (abs(float(loss_part) - loss_ref) / abs(loss_ref),
+                     float((mine - want).abs().max() / gref.abs().max()), n_fwd, n_bwd)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,depth', [(2, 2), (3, 2), (3, 1)])
+def test_band_scheme_with_relu_pool_and_taps_matches_autograd_over_gloo(world, depth):
+    """Algorithm-level CPU check of the sharded path's band logic (the CUDA path is held to the same statement on the
+    GPU by tests/test_gpu_sharding.py): loss and image gradient equal whole-image autograd to float64 rounding, with
+    3 + 4 exchanges at depth 1 and 1 + 2 at depth 2 for this five-step network."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_band_schedule_worker, args=(world, _free_port(), out, depth), nprocs=world, join=True)
+    assert sorted(out.keys()) == list(range(world))
+    for rank in range(world):
+        lerr, gerr, n_fwd, n_bwd = out[rank]
+        assert lerr < 1e-12 and gerr < 1e-12, (rank, lerr, gerr)
+        assert (n_fwd, n_bwd) == ((1, 2) if depth == 2 else (3, 4))
+
+
 def test_halo_schedule_of_the_vgg19_path():
     """parallel.halo_schedule: with one halo row every convolution but the first waits for its neighbours (12 forward +
     13 backward exchanges up to conv5_1); with two rows every second one does (6 + 7), and the steps in between run
