@@ -78,7 +78,7 @@ MIN_BAND_ROWS = 2 * ALIGN
 # Halo rows a band swaps per exchange on the channels-last path (halo_schedule): 2 = every second convolution runs on
 # redundantly computed edge rows instead of waiting for the neighbours (13 synchronisation points per closure instead
 # of 25, for 2 extra convolution rows per band and layer); 1 = an exchange before every convolution (round 1).
-HALO_DEPTH = int(os.environ.get('AST_HALO_DEPTH', '2'))
+HALO_DEPTH = min(max(int(os.environ.get('AST_HALO_DEPTH', '2')), 1), 2)
 
 
 class PyramidBands:
