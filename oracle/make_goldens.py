@@ -234,6 +234,49 @@ def golden_closure(math_utils, nst):
     print('closure.npz per-level', out['L2_per_level'])
 
 
+def golden_closure_odd(math_utils, nst):
+    """The same closure on a THREE-level pyramid with an odd middle level (66x90 -> 33x45 -> 16x22: the bicubic step
+    of nst.py:172-174 from 33x45 rounds down, its scale is 33/16, not 2, and its taps are no longer the constant
+    even-size ones), with other loss weights, again through the reference's own LossBuilder objects.  Kept in a file of its own
+    (closure_odd.npz) so that the older goldens stay byte-identical."""
+    import torch
+    import torch.nn.functional as F
+    import cv2
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import gatys_oracle as O
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    net, cidx, sidx = quiet(math_utils.prepare_model, 'vgg19', 'cpu')
+    h, w = 66, 90
+    content, style = O.synthetic_images(h, w, seed=21)
+    rng = np.random.default_rng(22)
+    init = np.clip(content * 0.4 + rng.uniform(0, 1, size=content.shape) * 0.6, 0, 1).astype(np.float32)
+    sizes = [(h, w), (h // 2, w // 2), (h // 4, w // 4)]
+    c_lv = [content] + [cv2.resize(content, (ww, hh), interpolation=cv2.INTER_CUBIC) for hh, ww in sizes[1:]]
+    s_lv = [style] + [cv2.resize(style, (ww, hh), interpolation=cv2.INTER_CUBIC) for hh, ww in sizes[1:]]
+    weights = (2e4, 3e4, 5e0)
+    builders = [quiet(nst.LossBuilder, cidx, sidx, nst.prepare_img(c, 'cpu'), nst.prepare_img(s, 'cpu'),
+                      net, *weights) for c, s in zip(c_lv, s_lv)]
+    out = {'init': init, 'weights': np.array(weights), 'sizes': np.array(sizes)}
+    for i in range(3):
+        out[f'content_l{i}'], out[f'style_l{i}'] = c_lv[i], s_lv[i]
+    img = nst.prepare_img(init, 'cpu').requires_grad_(True)
+    levels, total, per = [img], None, []
+    for i in range(3):
+        if i > 0:
+            p = levels[i - 1]
+            levels.append(F.interpolate(p, size=(p.shape[2] // 2, p.shape[3] // 2), mode='bicubic'))
+        t, c, s, v = builders[i].build(levels[i])
+        per.append([t.item(), c.item(), s.item(), v.item()])
+        total = t if total is None else 1.0 * total + t
+    total.backward()
+    assert tuple(levels[1].shape[-2:]) == (33, 45) and tuple(levels[2].shape[-2:]) == (16, 22)
+    out['per_level'] = np.array(per, dtype=np.float64)
+    out['total'] = np.float64(total.item())
+    out['grad'] = img.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, 'closure_odd.npz'), **out)
+    print('closure_odd.npz per-level', out['per_level'])
+
+
 def golden_driver(nst):
     """NeuralStyleTransfer.process (nst.py:123-208) end to end: Adam x4 and LBFGS x4 closures on
     one 64x96 level; records the yielded images (subsampled) and step counters."""
@@ -263,6 +306,10 @@ def golden_driver(nst):
 def main():
     os.makedirs(OUT, exist_ok=True)
     neural_nets, math_utils, nst = import_reference()
+    if sys.argv[1:] == ['closure_odd']:          # added in round 2: only this file, the others stay untouched
+        golden_closure_odd(math_utils, nst)
+        return
+    golden_closure_odd(math_utils, nst)
     golden_small_ops(math_utils, nst)
     golden_noise_init(nst)
     golden_closure(math_utils, nst)

@@ -36,9 +36,9 @@ def exact_convs():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic = old
 
 
-def product_closure(nst, net, cidx, sidx, c_levels, s_levels, init):
-    builders = [nst.LossBuilder(cidx, sidx, nst.prepare_img(c, dev()), nst.prepare_img(s, dev()), net, *WEIGHTS)
-                for c, s in zip(c_levels, s_levels)]
+def product_closure(nst, net, cidx, sidx, c_levels, s_levels, init, weights=None):
+    builders = [nst.LossBuilder(cidx, sidx, nst.prepare_img(c, dev()), nst.prepare_img(s, dev()), net,
+                                *(weights or WEIGHTS)) for c, s in zip(c_levels, s_levels)]
     from artstyletransfer_b200 import ops
     img = nst.prepare_img(init, dev()).requires_grad_(True)
     levels = [img]
@@ -84,6 +84,32 @@ def test_closure_vs_reference_golden_and_oracle(golden, seeded_vgg, nlev, precis
     assert abs(total - float(gd[f'L{nlev}_total'])) / float(gd[f'L{nlev}_total']) < 1e-3
     np.testing.assert_allclose(per, gd[f'L{nlev}_per_level'], rtol=2e-3)
     assert rel(grad, gd[f'L{nlev}_grad']) < 5e-3
+
+
+def test_closure_three_levels_with_an_odd_level_vs_reference_golden(golden, seeded_vgg):
+    """66x90 -> 33x45 -> 16x22: the second pyramid step is not an exact halving (general-ratio K6 resize and its
+    adjoint instead of the constant-tap K4 / K5), the 33x45 level pools with floor, other loss weights.  Against the
+    oracle's closure on the same device and against the unmodified reference's CPU result (closure_odd.npz)."""
+    from artstyletransfer_b200 import math_utils, neural_style_transfer as nst
+    gd = golden('closure_odd.npz')
+    weights = tuple(float(v) for v in gd['weights'])
+    c_lv = [gd[f'content_l{i}'] for i in range(3)]
+    s_lv = [gd[f'style_l{i}'] for i in range(3)]
+    net, cidx, sidx = math_utils.prepare_model('vgg19', dev())
+    total, per, grad = product_closure(nst, net, cidx, sidx, c_lv, s_lv, gd['init'], weights)
+    onet, ocidx, osidx = O.make_vgg19(1234)
+    onet = onet.to(dev())
+    targets = [O.torch_targets(onet, ocidx, osidx, torch.from_numpy(O.prepare_img(c)).to(dev()),
+                               torch.from_numpy(O.prepare_img(s)).to(dev())) for c, s in zip(c_lv, s_lv)]
+    ototal, oper, ograd = O.torch_closure(onet, ocidx, osidx, targets,
+                                          torch.from_numpy(O.prepare_img(gd['init'])).to(dev()), weights)
+    assert abs(total - float(ototal)) / float(ototal) < 1e-4
+    for i in range(3):
+        np.testing.assert_allclose(per[i], np.array([float(v) for v in oper[i]]), rtol=2e-4)
+    assert rel(grad, ograd.cpu().numpy()) < 2e-3
+    assert abs(total - float(gd['total'])) / float(gd['total']) < 1e-3
+    np.testing.assert_allclose(per, gd['per_level'], rtol=2e-3)
+    assert rel(grad, gd['grad']) < 5e-3
 
 
 def test_vgg_conv4_2_is_relu4_2(seeded_vgg):
